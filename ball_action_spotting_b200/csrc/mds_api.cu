@@ -1,0 +1,733 @@
+// C-ABI of libmds_b200.so: packed-weight handle, the MultiDimStacker layer program, and per-kernel entry points.
+// See include/mds_b200.h for the contract of every exported function.
+#include "../../include/mds_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv3x3.cuh"
+#include "dwconv.cuh"
+#include "gemm1x1.cuh"
+#include "se_head.cuh"
+#include "stem.cuh"
+
+using namespace mds;
+
+// --------------------------------------------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local long long g_launches = 0;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return fail(MDS_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define LAUNCH_CHECK(name)                                                                                  \
+    do {                                                                                                    \
+        ++g_launches;                                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                                \
+        if (e_ != cudaSuccess) return fail(MDS_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e_));    \
+    } while (0)
+#define TRY(expr)                \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+extern "C" const char* mds_last_error(void) { return g_err.c_str(); }
+extern "C" long long mds_launch_count(int reset) {
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+// ---- optional per-launch CUDA-event profiling (bench.py roofline; off by default) ----
+struct ProfRec { int kind, tag; cudaEvent_t a, b; };
+static thread_local bool g_prof_on = false;
+static thread_local int g_prof_tag = -1;
+static thread_local std::vector<ProfRec> g_prof;
+struct ProfScope {
+    cudaStream_t st; bool on;
+    ProfScope(int kind, cudaStream_t s) : st(s), on(g_prof_on) {
+        if (!on) return;
+        ProfRec r; r.kind = kind; r.tag = g_prof_tag;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        g_prof.push_back(r);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(g_prof.back().b, st); }
+};
+extern "C" int mds_profile_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+    return MDS_OK;
+}
+extern "C" int mds_profile_end(int* kinds, int* tags, float* ms, int capacity, int* count) {
+    g_prof_on = false;
+    int n = 0;
+    for (auto& r : g_prof) {
+        cudaError_t e = cudaEventSynchronize(r.b);
+        float t = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+        if (e != cudaSuccess) return fail(MDS_ERR_CUDA, "profile: %s", cudaGetErrorString(e));
+        if (n < capacity && kinds && tags && ms) { kinds[n] = r.kind; tags[n] = r.tag; ms[n] = t; }
+        ++n;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    if (count) *count = n;
+    return MDS_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// kernel launchers
+// --------------------------------------------------------------------------------------------------------------
+static int launch_stem(const MdsFrames& f, int n, const float* w, const float* bias, __half* out, cudaStream_t st) {
+    if (f.H % 2 || f.W % 2 || f.H <= 0 || f.W <= 0) return fail(MDS_ERR_INVALID, "stem: H, W must be even");
+    if (n <= 0) return MDS_OK;
+    StemParams p;
+    p.in = f.data; p.img_stride = f.img_stride; p.plane_stride = f.plane_stride;
+    p.stored_h = f.stored_h; p.pad_top = f.pad_top; p.H = f.H; p.W = f.W; p.hflip = f.hflip;
+    p.divisor = f.dtype == 0 ? 255.0f : 1.0f;
+    p.w = w; p.bias = bias; p.out = out;
+    dim3 grid((f.W / 2 + kStemTW - 1) / kStemTW, (f.H / 2 + kStemTH - 1) / kStemTH, n);
+    ProfScope ps(MDS_KIND_STEM, st);
+    if (f.dtype == 0) stem_kernel<uint8_t><<<grid, 256, 0, st>>>(p);
+    else if (f.dtype == 1) stem_kernel<float><<<grid, 256, 0, st>>>(p);
+    else return fail(MDS_ERR_INVALID, "stem: dtype must be 0 (uint8) or 1 (float32)");
+    LAUNCH_CHECK("stem");
+    return MDS_OK;
+}
+
+template <int CIN, int CMID, int STRIDE, int CPROJ, bool RES, int MINB>
+static int launch_conv3_t(const Conv3Params& p, cudaStream_t st) {
+    using Cfg = Conv3Cfg<CIN, CMID, STRIDE, CPROJ, RES>;
+    auto kern = conv3x3_kernel<CIN, CMID, STRIDE, CPROJ, RES, MINB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const int tiles = ((p.Wo + Cfg::TW - 1) / Cfg::TW) * ((p.Ho + Cfg::TH - 1) / Cfg::TH) * p.n;
+    if (tiles <= 0) return MDS_OK;
+    int grid = num_sms() * MINB;
+    if (grid > tiles) grid = tiles;
+    ProfScope ps(MDS_KIND_CONV3X3, st);
+    kern<<<grid, 256, Cfg::SMEM, st>>>(p);
+    LAUNCH_CHECK("conv3x3");
+    return MDS_OK;
+}
+
+static int launch_conv3(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2,
+                        const float* b2, int n, int H, int W, int cin, int cmid, int stride, int cproj, int res,
+                        cudaStream_t st) {
+    Conv3Params p;
+    p.in = in; p.out = out; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
+    p.n = n; p.H = H; p.W = W;
+    p.Ho = (H + stride - 1) / stride; p.Wo = (W + stride - 1) / stride;
+    if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv3x3: stride-2 input must be even");
+#define C3CASE(CI, CM, S, CP, R, MB) \
+    if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0)) return launch_conv3_t<CI, CM, S, CP, R, MB>(p, st);
+    C3CASE(32, 16, 1, 0, false, 4)      // blocks.0.0  ConvBnAct
+    C3CASE(16, 64, 2, 32, false, 2)     // blocks.1.0  EdgeResidual s2
+    C3CASE(32, 128, 1, 32, true, 1)     // blocks.1.1
+    C3CASE(32, 128, 2, 48, false, 1)    // blocks.2.0
+    C3CASE(48, 192, 1, 48, true, 1)     // blocks.2.1
+#undef C3CASE
+    return fail(MDS_ERR_INVALID, "conv3x3: unsupported shape cin=%d cmid=%d stride=%d cproj=%d res=%d", cin, cmid, stride, cproj, res);
+}
+
+template <int BN, bool GATED>
+static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm1x1_kernel<BN, GATED>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const int tiles_per_img = (p.rows_per_img + kGemmBM - 1) / kGemmBM;
+    dim3 grid((p.N + BN - 1) / BN, tiles_per_img * p.n_img);
+    if (grid.y > 65535) return fail(MDS_ERR_INVALID, "gemm1x1: too many M tiles (%u)", grid.y);
+    ProfScope ps(MDS_KIND_GEMM1X1, st);
+    kern<<<grid, 256, Cfg::SMEM, st>>>(p);
+    LAUNCH_CHECK("gemm1x1");
+    return MDS_OK;
+}
+
+static int launch_gemm(const __half* A, const __half* W, const float* bias, const __half* res, const __half* gate,
+                       __half* C, long long rows_per_img, int n_img, int N, int K, int act, cudaStream_t st) {
+    if (K % 16 || N % 16 || K > 1152) return fail(MDS_ERR_INVALID, "gemm1x1: N, K must be multiples of 16, K <= 1152 (N=%d K=%d)", N, K);
+    if (rows_per_img <= 0 || n_img <= 0) return MDS_OK;
+    // The M-tile index lives in gridDim.y (<= 65535): split very large ungated problems into row slabs.
+    const long long max_rows = 65535LL * kGemmBM;
+    if (gate == nullptr && rows_per_img * n_img > max_rows) {
+        long long total = rows_per_img * n_img;
+        for (long long r0 = 0; r0 < total; r0 += max_rows) {
+            long long rows = total - r0 < max_rows ? total - r0 : max_rows;
+            TRY(launch_gemm(A + r0 * K, W, bias, res ? res + r0 * N : nullptr, nullptr, C + r0 * N, rows, 1, N, K, act, st));
+        }
+        return MDS_OK;
+    }
+    GemmParams p;
+    p.A = A; p.W = W; p.bias = bias; p.res = res; p.gate = gate; p.C = C;
+    p.N = N; p.K = K; p.act = act;
+    if (gate == nullptr) { p.rows_per_img = (int)(rows_per_img * n_img); p.n_img = 1; }
+    else { p.rows_per_img = (int)rows_per_img; p.n_img = n_img; }
+#define GCASE(BN_)                                                      \
+    if (N % BN_ == 0) {                                                 \
+        if (gate) return launch_gemm_t<BN_, true>(p, st);               \
+        return launch_gemm_t<BN_, false>(p, st);                        \
+    }
+    GCASE(128) GCASE(112) GCASE(96) GCASE(64)
+#undef GCASE
+    return fail(MDS_ERR_INVALID, "gemm1x1: N=%d is not a multiple of 128/112/96/64", N);
+}
+
+static int launch_dw(const __half* in, __half* out, const float* w, const float* bias, float* sums, int n, int T,
+                     int H, int W, int C, int kt, int stride, cudaStream_t st) {
+    if (C % 4 || C > 4096) return fail(MDS_ERR_INVALID, "dwconv: C must be a multiple of 4");
+    if (!((kt == 1 && (stride == 1 || stride == 2)) || (kt == 3 && stride == 1)))
+        return fail(MDS_ERR_INVALID, "dwconv: unsupported kt=%d stride=%d", kt, stride);
+    if (kt == 1 && T != 1) return fail(MDS_ERR_INVALID, "dwconv 2D: T must be 1");
+    if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "dwconv: stride-2 input must be even");
+    if (n <= 0) return MDS_OK;
+    DwParams p;
+    p.in = in; p.out = out; p.w = w; p.bias = bias; p.sums = sums;
+    p.n = n; p.T = T; p.H = H; p.W = W; p.C = C;
+    p.Ho = H / stride; p.Wo = W / stride;
+    const int bx = (p.Wo * (C / 4) + 255) / 256;
+    // enough CTAs to fill the machine a few times over: split rows when the batch is small
+    int chunks = 1;
+    const long long base = (long long)bx * n * T;
+    const long long want = (long long)num_sms() * 8;
+    if (base < want) {
+        chunks = (int)((want + base - 1) / base);
+        if (chunks > p.Ho / 4) chunks = p.Ho / 4 > 0 ? p.Ho / 4 : 1;
+    }
+    p.rows_per_chunk = (p.Ho + chunks - 1) / chunks;
+    p.chunks = (p.Ho + p.rows_per_chunk - 1) / p.rows_per_chunk;
+    dim3 grid(bx, p.chunks * T, n);
+    const size_t smem = (size_t)C * sizeof(float);
+    ProfScope ps(kt == 1 ? MDS_KIND_DWCONV2D : MDS_KIND_DWCONV3D, st);
+    if (kt == 1) {
+        if (stride == 1) dwconv2d_kernel<1><<<grid, 256, smem, st>>>(p);
+        else dwconv2d_kernel<2><<<grid, 256, smem, st>>>(p);
+    } else {
+        dwconv3d_kernel<<<grid, 256, smem, st>>>(p);
+    }
+    LAUNCH_CHECK("dwconv");
+    return MDS_OK;
+}
+
+static int launch_se(float* sums, const float* w1, const float* b1, const float* w2t, const float* b2, __half* gate,
+                     int n, int C, int rd, float inv_count, cudaStream_t st) {
+    if (n <= 0) return MDS_OK;
+    if (C > 4096 || rd > 256) return fail(MDS_ERR_INVALID, "se_fc: C/rd too large");
+    SeParams p;
+    p.sums = sums; p.w1 = w1; p.b1 = b1; p.w2t = w2t; p.b2 = b2; p.gate = gate; p.C = C; p.rd = rd; p.inv_count = inv_count;
+    ProfScope ps(MDS_KIND_SE_FC, st);
+    se_fc_kernel<<<n, 256, (size_t)(C + rd) * sizeof(float), st>>>(p);
+    LAUNCH_CHECK("se_fc");
+    return MDS_OK;
+}
+
+static int launch_gem(const __half* x, float* feat, int b, int T, int P, int C, float pw, float eps, cudaStream_t st) {
+    if (C % 8 || C > 256 || C < 32) return fail(MDS_ERR_INVALID, "gem: C must be a multiple of 8 in [32, 256]");
+    if (b <= 0) return MDS_OK;
+    GemParams g;
+    g.x = x; g.feat = feat; g.T = T; g.P = P; g.C = C; g.p = pw; g.eps = eps;
+    ProfScope ps(MDS_KIND_HEAD, st);
+    gem_kernel<<<dim3(T, b), 256, 0, st>>>(g);
+    LAUNCH_CHECK("gem");
+    return MDS_OK;
+}
+
+static int launch_linear(const float* feat, const float* w, const float* bias, float* out, int b, int F, int k, int sig,
+                         cudaStream_t st) {
+    if (b <= 0) return MDS_OK;
+    ProfScope ps(MDS_KIND_HEAD, st);
+    linear_head_kernel<<<b, 256, 0, st>>>(feat, w, bias, out, F, k, sig);
+    LAUNCH_CHECK("linear_head");
+    return MDS_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// handle: packed weights + layer program
+// --------------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct Block2d {
+    char kind;   // 'c' ConvBnAct, 'e' EdgeResidual, 'i' InvertedResidual
+    int cin, mid, cout, stride, rd;
+    bool skip;
+    const __half *w1 = nullptr, *w2 = nullptr, *wpw = nullptr, *wpwl = nullptr;
+    const float *b1 = nullptr, *b2 = nullptr, *bpw = nullptr, *bpwl = nullptr;
+    const float *wdw = nullptr, *bdw = nullptr, *se_w1 = nullptr, *se_b1 = nullptr, *se_w2t = nullptr, *se_b2 = nullptr;
+};
+struct Block3d {
+    const __half *wpw, *wpwl;
+    const float *bpw, *bpwl, *wdw, *bdw, *se_w1, *se_b1, *se_w2t, *se_b2;
+};
+
+struct MdsHandle {
+    MdsConfig cfg;
+    std::map<std::string, DevBuf> tensors;
+    bool committed = false;
+    const float *stem_w = nullptr, *stem_b = nullptr;
+    std::vector<Block2d> blocks;
+    const __half *proj2d_w = nullptr, *proj3d_w = nullptr;
+    const float *proj2d_b = nullptr, *proj3d_b = nullptr;
+    std::vector<Block3d> blocks3d;
+    float gem_p = 3.0f;
+    const float *cls_w = nullptr, *cls_b = nullptr;
+    int T() const { return cfg.num_frames / cfg.stack_size; }
+    int mid3d() const { return cfg.num_3d_features * cfg.expansion_3d_ratio; }
+    int rd3d() const { return mid3d() / cfg.se_reduce_3d_ratio; }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) { cudaSetDevice(dev); changed = true; }
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+static const int kStageDefs[6][6] = {
+    // kind(0 c,1 e,2 i), repeats, stride, expand, cout, se (x100)
+    {0, 1, 1, 1, 16, 0}, {1, 2, 2, 4, 32, 0}, {1, 2, 2, 4, 48, 0}, {2, 3, 2, 4, 96, 25}, {2, 5, 1, 6, 112, 25}, {2, 8, 2, 6, 192, 25}};
+
+extern "C" int mds_create(const MdsConfig* cfg, MdsHandle** out) {
+    if (!cfg || !out) return fail(MDS_ERR_INVALID, "mds_create: null argument");
+    if (cfg->stack_size != 3) return fail(MDS_ERR_INVALID, "stack_size must be 3 (got %d)", cfg->stack_size);
+    if (cfg->num_frames <= 0 || cfg->num_frames % cfg->stack_size)
+        return fail(MDS_ERR_INVALID, "num_frames (%d) must be a positive multiple of stack_size", cfg->num_frames);
+    if (cfg->num_3d_features != 192) return fail(MDS_ERR_INVALID, "num_3d_features must be 192");
+    if (cfg->num_3d_stack_proj % 64 || cfg->num_3d_stack_proj > 256 || cfg->num_3d_stack_proj <= 0)
+        return fail(MDS_ERR_INVALID, "num_3d_stack_proj must be a multiple of 64, <= 256");
+    const int mid = cfg->num_3d_features * cfg->expansion_3d_ratio;
+    if (mid % 64 || mid > 1152 || cfg->se_reduce_3d_ratio <= 0 || mid / cfg->se_reduce_3d_ratio <= 0)
+        return fail(MDS_ERR_INVALID, "unsupported 3D expansion / SE ratio");
+    if (cfg->num_classes <= 0 || cfg->num_3d_blocks < 0) return fail(MDS_ERR_INVALID, "bad num_classes / num_3d_blocks");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(MDS_ERR_INVALID, "device %d out of range", cfg->device);
+    MdsHandle* h = new MdsHandle();
+    h->cfg = *cfg;
+    if (h->cfg.chunk_images <= 0) h->cfg.chunk_images = 8;
+    *out = h;
+    return MDS_OK;
+}
+
+extern "C" int mds_destroy(MdsHandle* h) {
+    if (!h) return MDS_OK;
+    DeviceGuard g(h->cfg.device);
+    for (auto& kv : h->tensors) cudaFree(kv.second.ptr);
+    delete h;
+    return MDS_OK;
+}
+
+extern "C" int mds_weights_add(MdsHandle* h, const char* name, const void* host_data, size_t nbytes) {
+    if (!h || !name || !host_data || nbytes == 0) return fail(MDS_ERR_INVALID, "mds_weights_add: bad argument");
+    DeviceGuard g(h->cfg.device);
+    DevBuf& b = h->tensors[name];
+    if (b.ptr && b.bytes != nbytes) { cudaFree(b.ptr); b.ptr = nullptr; }
+    if (!b.ptr) CUDA_TRY(cudaMalloc(&b.ptr, nbytes));
+    b.bytes = nbytes;
+    CUDA_TRY(cudaMemcpy(b.ptr, host_data, nbytes, cudaMemcpyHostToDevice));
+    h->committed = false;
+    return MDS_OK;
+}
+
+template <typename T>
+static int get_tensor(MdsHandle* h, const std::string& name, size_t count, const T** out) {
+    auto it = h->tensors.find(name);
+    if (it == h->tensors.end()) return fail(MDS_ERR_WEIGHTS, "missing tensor '%s'", name.c_str());
+    if (it->second.bytes != count * sizeof(T))
+        return fail(MDS_ERR_WEIGHTS, "tensor '%s': expected %zu bytes, got %zu", name.c_str(), count * sizeof(T), it->second.bytes);
+    *out = reinterpret_cast<const T*>(it->second.ptr);
+    return MDS_OK;
+}
+
+extern "C" int mds_weights_commit(MdsHandle* h) {
+    if (!h) return fail(MDS_ERR_INVALID, "null handle");
+    DeviceGuard g(h->cfg.device);
+    h->blocks.clear();
+    h->blocks3d.clear();
+    TRY(get_tensor(h, "stem.w", 27 * 32, &h->stem_w));
+    TRY(get_tensor(h, "stem.b", 32, &h->stem_b));
+    int cin = 32;
+    for (int si = 0; si < 6; ++si) {
+        const int* d = kStageDefs[si];
+        for (int bi = 0; bi < d[1]; ++bi) {
+            Block2d b;
+            b.kind = d[0] == 0 ? 'c' : d[0] == 1 ? 'e' : 'i';
+            b.cin = cin; b.cout = d[4]; b.stride = bi == 0 ? d[2] : 1; b.mid = cin * d[3];
+            b.rd = d[5] ? (cin * d[5] + 50) / 100 : 0;
+            b.skip = b.kind != 'c' && b.stride == 1 && b.cin == b.cout;
+            char pre[32];
+            snprintf(pre, sizeof(pre), "b%d.%d.", si, bi);
+            const std::string p(pre);
+            if (b.kind == 'c') {
+                TRY(get_tensor(h, p + "c3.w", (size_t)b.cout * 9 * b.cin, &b.w1));
+                TRY(get_tensor(h, p + "c3.b", b.cout, &b.b1));
+            } else if (b.kind == 'e') {
+                TRY(get_tensor(h, p + "c3.w", (size_t)b.mid * 9 * b.cin, &b.w1));
+                TRY(get_tensor(h, p + "c3.b", b.mid, &b.b1));
+                TRY(get_tensor(h, p + "pwl.w", (size_t)b.cout * b.mid, &b.w2));
+                TRY(get_tensor(h, p + "pwl.b", b.cout, &b.b2));
+            } else {
+                TRY(get_tensor(h, p + "pw.w", (size_t)b.mid * b.cin, &b.wpw));
+                TRY(get_tensor(h, p + "pw.b", b.mid, &b.bpw));
+                TRY(get_tensor(h, p + "dw.w", (size_t)9 * b.mid, &b.wdw));
+                TRY(get_tensor(h, p + "dw.b", b.mid, &b.bdw));
+                TRY(get_tensor(h, p + "se.w1", (size_t)b.rd * b.mid, &b.se_w1));
+                TRY(get_tensor(h, p + "se.b1", b.rd, &b.se_b1));
+                TRY(get_tensor(h, p + "se.w2t", (size_t)b.rd * b.mid, &b.se_w2t));
+                TRY(get_tensor(h, p + "se.b2", b.mid, &b.se_b2));
+                TRY(get_tensor(h, p + "pwl.w", (size_t)b.cout * b.mid, &b.wpwl));
+                TRY(get_tensor(h, p + "pwl.b", b.cout, &b.bpwl));
+            }
+            h->blocks.push_back(b);
+            cin = b.cout;
+        }
+    }
+    const int c3 = h->cfg.num_3d_features, mid = h->mid3d(), rd = h->rd3d(), pj = h->cfg.num_3d_stack_proj;
+    TRY(get_tensor(h, "proj2d.w", (size_t)c3 * 192, &h->proj2d_w));
+    TRY(get_tensor(h, "proj2d.b", c3, &h->proj2d_b));
+    for (int i = 0; i < h->cfg.num_3d_blocks; ++i) {
+        Block3d b;
+        char pre[32];
+        snprintf(pre, sizeof(pre), "c3d.%d.", i);
+        const std::string p(pre);
+        TRY(get_tensor(h, p + "pw.w", (size_t)mid * c3, &b.wpw));
+        TRY(get_tensor(h, p + "pw.b", mid, &b.bpw));
+        TRY(get_tensor(h, p + "dw.w", (size_t)27 * mid, &b.wdw));
+        TRY(get_tensor(h, p + "dw.b", mid, &b.bdw));
+        TRY(get_tensor(h, p + "se.w1", (size_t)rd * mid, &b.se_w1));
+        TRY(get_tensor(h, p + "se.b1", rd, &b.se_b1));
+        TRY(get_tensor(h, p + "se.w2t", (size_t)rd * mid, &b.se_w2t));
+        TRY(get_tensor(h, p + "se.b2", mid, &b.se_b2));
+        TRY(get_tensor(h, p + "pwl.w", (size_t)c3 * mid, &b.wpwl));
+        TRY(get_tensor(h, p + "pwl.b", c3, &b.bpwl));
+        h->blocks3d.push_back(b);
+    }
+    TRY(get_tensor(h, "proj3d.w", (size_t)pj * c3, &h->proj3d_w));
+    TRY(get_tensor(h, "proj3d.b", pj, &h->proj3d_b));
+    const float* gp = nullptr;
+    TRY(get_tensor(h, "gem.p", 1, &gp));
+    CUDA_TRY(cudaMemcpy(&h->gem_p, gp, sizeof(float), cudaMemcpyDeviceToHost));
+    if (!(h->gem_p > 0.f)) return fail(MDS_ERR_WEIGHTS, "gem.p must be > 0");
+    TRY(get_tensor(h, "cls.w", (size_t)h->cfg.num_classes * pj * h->T(), &h->cls_w));
+    TRY(get_tensor(h, "cls.b", h->cfg.num_classes, &h->cls_b));
+    h->committed = true;
+    return MDS_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// workspace
+// --------------------------------------------------------------------------------------------------------------
+struct Arena {
+    char* base;
+    size_t cap, off = 0;
+    bool overflow = false;
+    Arena(void* p, size_t c) : base(reinterpret_cast<char*>(p)), cap(c) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (off + bytes > cap) { overflow = true; return nullptr; }
+        T* r = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return r;
+    }
+};
+static size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
+
+struct Sizes2d {
+    size_t stream_elems, mid1_elems, mid2_elems;   // per image
+};
+static Sizes2d sizes2d(int H, int W) {
+    Sizes2d s{0, 0, 0};
+    int h = H / 2, w = W / 2;
+    auto upd = [](size_t& a, size_t b) { if (b > a) a = b; };
+    upd(s.stream_elems, (size_t)h * w * 32);
+    int cin = 32;
+    for (int si = 0; si < 6; ++si) {
+        const int* d = kStageDefs[si];
+        for (int bi = 0; bi < d[1]; ++bi) {
+            int stride = bi == 0 ? d[2] : 1, mid = cin * d[3], cout = d[4];
+            int ho = h / stride, wo = w / stride;
+            if (d[0] == 2) {
+                upd(s.mid1_elems, (size_t)h * w * mid);
+                upd(s.mid2_elems, (size_t)ho * wo * mid);
+            }
+            upd(s.stream_elems, (size_t)ho * wo * cout);
+            h = ho; w = wo; cin = cout;
+        }
+    }
+    return s;
+}
+
+static size_t ws2d_bytes(const MdsHandle* h, int H, int W, int n_images) {
+    int cs = n_images < h->cfg.chunk_images ? n_images : h->cfg.chunk_images;
+    if (cs <= 0) cs = 1;
+    Sizes2d s = sizes2d(H, W);
+    return 2 * al256(s.stream_elems * cs * 2) + al256(s.mid1_elems * cs * 2) + al256(s.mid2_elems * cs * 2) +
+           al256((size_t)cs * 1152 * 4) + al256((size_t)cs * 1152 * 2);
+}
+static size_t ws3d_bytes(const MdsHandle* h, int b, int P) {
+    const size_t rows = (size_t)b * h->T() * P;
+    return 2 * al256(rows * h->cfg.num_3d_features * 2) + 2 * al256(rows * h->mid3d() * 2) +
+           al256((size_t)b * h->mid3d() * 4) + al256((size_t)b * h->mid3d() * 2);
+}
+static size_t wshead_bytes(const MdsHandle* h, int b) { return al256((size_t)b * h->cfg.num_3d_stack_proj * h->T() * 4); }
+
+extern "C" size_t mds_workspace_bytes(const MdsHandle* h, int H, int W, int n_images, int n_stacks) {
+    if (!h) return 0;
+    const int P = (H / 32) * (W / 32);
+    const size_t rows = (size_t)n_stacks * h->T() * P;
+    size_t full = ws2d_bytes(h, H, W, n_images) + al256(rows * 192 * 2) + ws3d_bytes(h, n_stacks, P) +
+                  al256(rows * h->cfg.num_3d_stack_proj * 2) + wshead_bytes(h, n_stacks);
+    return full + 4096;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// forward passes
+// --------------------------------------------------------------------------------------------------------------
+static int check_ready(MdsHandle* h) {
+    if (!h) return fail(MDS_ERR_INVALID, "null handle");
+    if (!h->committed) return fail(MDS_ERR_WEIGHTS, "weights not committed");
+    return MDS_OK;
+}
+
+static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __half* feats_out, Arena& ar, cudaStream_t st) {
+    if (fr.H % 32 || fr.W % 32 || fr.H <= 0 || fr.W <= 0)
+        return fail(MDS_ERR_INVALID, "forward_2d: H (%d) and W (%d) must be positive multiples of 32", fr.H, fr.W);
+    if (fr.stored_h + fr.pad_top > fr.H || fr.pad_top < 0 || fr.stored_h <= 0)
+        return fail(MDS_ERR_INVALID, "forward_2d: frame rows (%d + pad %d) exceed H=%d", fr.stored_h, fr.pad_top, fr.H);
+    if (n_images <= 0) return MDS_OK;
+    const int cs_max = n_images < h->cfg.chunk_images ? n_images : h->cfg.chunk_images;
+    const Sizes2d sz = sizes2d(fr.H, fr.W);
+    __half* X[2];
+    X[0] = ar.take<__half>(sz.stream_elems * cs_max);
+    X[1] = ar.take<__half>(sz.stream_elems * cs_max);
+    __half* M1 = ar.take<__half>(sz.mid1_elems * cs_max);
+    __half* M2 = ar.take<__half>(sz.mid2_elems * cs_max);
+    float* sums = ar.take<float>((size_t)cs_max * 1152);
+    __half* gate = ar.take<__half>((size_t)cs_max * 1152);
+    if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_2d: workspace too small");
+    CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)cs_max * 1152 * sizeof(float), st));
+    const int elem = fr.dtype == 0 ? 1 : 4;
+    const int P = (fr.H / 32) * (fr.W / 32);
+
+    for (int i0 = 0; i0 < n_images; i0 += cs_max) {
+        const int cs = n_images - i0 < cs_max ? n_images - i0 : cs_max;
+        MdsFrames f = fr;
+        f.data = reinterpret_cast<const char*>(fr.data) + (size_t)i0 * fr.img_stride * elem;
+        int hh = fr.H / 2, ww = fr.W / 2, cur = 0;
+        g_prof_tag = 0;
+        TRY(launch_stem(f, cs, h->stem_w, h->stem_b, X[0], st));
+        for (const Block2d& b : h->blocks) {
+            ++g_prof_tag;
+            const int ho = hh / b.stride, wo = ww / b.stride;
+            if (b.kind == 'c') {
+                TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, nullptr, nullptr, cs, hh, ww, b.cin, b.cout, b.stride, 0, 0, st));
+            } else if (b.kind == 'e') {
+                TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, b.w2, b.b2, cs, hh, ww, b.cin, b.mid, b.stride, b.cout, b.skip, st));
+            } else {
+                TRY(launch_gemm(X[cur], b.wpw, b.bpw, nullptr, nullptr, M1, (long long)hh * ww, cs, b.mid, b.cin, 1, st));
+                TRY(launch_dw(M1, M2, b.wdw, b.bdw, sums, cs, 1, hh, ww, b.mid, 1, b.stride, st));
+                TRY(launch_se(sums, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, cs, b.mid, b.rd, 1.0f / (float)(ho * wo), st));
+                TRY(launch_gemm(M2, b.wpwl, b.bpwl, b.skip ? X[cur] : nullptr, gate, X[cur ^ 1], (long long)ho * wo, cs, b.cout, b.mid, 0, st));
+            }
+            cur ^= 1; hh = ho; ww = wo;
+        }
+        ++g_prof_tag;
+        TRY(launch_gemm(X[cur], h->proj2d_w, h->proj2d_b, nullptr, nullptr, feats_out + (size_t)i0 * P * 192,
+                        (long long)P, cs, h->cfg.num_3d_features, 192, 1, st));
+    }
+    return MDS_OK;
+}
+
+static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int fw, __half* out, Arena& ar, cudaStream_t st) {
+    if (b <= 0) return MDS_OK;
+    if (fh <= 0 || fw <= 0) return fail(MDS_ERR_INVALID, "forward_3d: bad feature map size %dx%d", fh, fw);
+    const int P = fh * fw;
+    const int T = h->T(), c3 = h->cfg.num_3d_features, mid = h->mid3d(), rd = h->rd3d();
+    const size_t rows = (size_t)b * T * P;
+    __half* Y[2];
+    Y[0] = ar.take<__half>(rows * c3);
+    Y[1] = ar.take<__half>(rows * c3);
+    __half* M1 = ar.take<__half>(rows * mid);
+    __half* M2 = ar.take<__half>(rows * mid);
+    float* sums = ar.take<float>((size_t)b * mid);
+    __half* gate = ar.take<__half>((size_t)b * mid);
+    if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_3d: workspace too small");
+    CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)b * mid * sizeof(float), st));
+    const __half* x = feats;
+    int nxt = 0;
+    // the 2D features are [b][T][h][w][C] already, i.e. the reference's transpose(1,2) is a no-op in NDHWC
+    // (multidim_stacker.py:224,226)
+    g_prof_tag = 100;
+    for (const Block3d& blk : h->blocks3d) {
+        ++g_prof_tag;
+        TRY(launch_gemm(x, blk.wpw, blk.bpw, nullptr, nullptr, M1, (long long)T * P, b, mid, c3, 1, st));
+        TRY(launch_dw(M1, M2, blk.wdw, blk.bdw, sums, b, T, fh, fw, mid, 3, 1, st));
+        TRY(launch_se(sums, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, b, mid, rd, 1.0f / (float)((size_t)T * P), st));
+        TRY(launch_gemm(M2, blk.wpwl, blk.bpwl, x, gate, Y[nxt], (long long)T * P, b, c3, mid, 0, st));
+        x = Y[nxt];
+        nxt ^= 1;
+    }
+    g_prof_tag = 150;
+    TRY(launch_gemm(x, h->proj3d_w, h->proj3d_b, nullptr, nullptr, out, (long long)T * P, b, h->cfg.num_3d_stack_proj, c3, 1, st));
+    return MDS_OK;
+}
+
+static int forward_head_impl(MdsHandle* h, const __half* x, int b, int P, float* logits, int sig, Arena& ar, cudaStream_t st) {
+    if (b <= 0) return MDS_OK;
+    const int T = h->T(), pj = h->cfg.num_3d_stack_proj;
+    float* feat = ar.take<float>((size_t)b * T * pj);
+    if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_head: workspace too small");
+    g_prof_tag = 200;
+    TRY(launch_gem(x, feat, b, T, P, pj, h->gem_p, 1e-6f, st));
+    TRY(launch_linear(feat, h->cls_w, h->cls_b, logits, b, T * pj, h->cfg.num_classes, sig, st));
+    return MDS_OK;
+}
+
+extern "C" int mds_forward_2d(MdsHandle* h, const MdsFrames* frames, int n_images, void* feats_out, void* ws,
+                              size_t ws_bytes, void* stream) {
+    TRY(check_ready(h));
+    if (!frames || !frames->data || !feats_out || !ws) return fail(MDS_ERR_INVALID, "forward_2d: null argument");
+    DeviceGuard g(h->cfg.device);
+    Arena ar(ws, ws_bytes);
+    return forward_2d_impl(h, *frames, n_images, reinterpret_cast<__half*>(feats_out), ar, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mds_forward_3d(MdsHandle* h, const void* feats, int b, int fh, int fw, void* out, void* ws, size_t ws_bytes,
+                              void* stream) {
+    TRY(check_ready(h));
+    if (!feats || !out || !ws) return fail(MDS_ERR_INVALID, "forward_3d: null argument");
+    DeviceGuard g(h->cfg.device);
+    Arena ar(ws, ws_bytes);
+    return forward_3d_impl(h, reinterpret_cast<const __half*>(feats), b, fh, fw, reinterpret_cast<__half*>(out), ar,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mds_forward_head(MdsHandle* h, const void* x, int b, int P, float* logits, int apply_sigmoid, void* ws,
+                                size_t ws_bytes, void* stream) {
+    TRY(check_ready(h));
+    if (!x || !logits || !ws) return fail(MDS_ERR_INVALID, "forward_head: null argument");
+    DeviceGuard g(h->cfg.device);
+    Arena ar(ws, ws_bytes);
+    return forward_head_impl(h, reinterpret_cast<const __half*>(x), b, P, logits, apply_sigmoid, ar,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mds_forward(MdsHandle* h, const MdsFrames* frames, int b, float* logits, int apply_sigmoid, void* ws,
+                           size_t ws_bytes, void* stream) {
+    TRY(check_ready(h));
+    if (!frames || !frames->data || !logits || !ws) return fail(MDS_ERR_INVALID, "forward: null argument");
+    DeviceGuard g(h->cfg.device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Arena ar(ws, ws_bytes);
+    const int T = h->T();
+    const int h3 = frames->H / 32, w3 = frames->W / 32, P = h3 * w3;
+    const size_t rows = (size_t)b * T * P;
+    __half* feats = ar.take<__half>(rows * 192);
+    __half* out3d = ar.take<__half>(rows * h->cfg.num_3d_stack_proj);
+    if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward: workspace too small");
+    TRY(forward_2d_impl(h, *frames, b * T, feats, ar, st));
+    // the 2D scratch is dead now: re-use the arena from the same mark for the 3D stage
+    Arena ar3(ar.base + al256(rows * 192 * 2) + al256(rows * h->cfg.num_3d_stack_proj * 2),
+              ws_bytes - al256(rows * 192 * 2) - al256(rows * h->cfg.num_3d_stack_proj * 2));
+    TRY(forward_3d_impl(h, feats, b, h3, w3, out3d, ar3, st));
+    TRY(forward_head_impl(h, out3d, b, P, logits, apply_sigmoid, ar3, st));
+    return MDS_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// converters + per-kernel entry points
+// --------------------------------------------------------------------------------------------------------------
+extern "C" int mds_nchw32_to_nhwc16(const float* src, void* dst, int n, int C, int P, void* stream) {
+    if (n <= 0) return MDS_OK;
+    if (n > 65535) return fail(MDS_ERR_INVALID, "converter: n too large");
+    dim3 grid((P + 31) / 32, (C + 31) / 32, n);
+    nchw32_to_nhwc16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<__half*>(dst), C, P);
+    LAUNCH_CHECK("nchw32_to_nhwc16");
+    return MDS_OK;
+}
+extern "C" int mds_nhwc16_to_nchw32(const void* src, float* dst, int n, int C, int P, void* stream) {
+    if (n <= 0) return MDS_OK;
+    if (n > 65535) return fail(MDS_ERR_INVALID, "converter: n too large");
+    dim3 grid((P + 31) / 32, (C + 31) / 32, n);
+    nhwc16_to_nchw32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __half*>(src), dst, C, P);
+    LAUNCH_CHECK("nhwc16_to_nchw32");
+    return MDS_OK;
+}
+
+extern "C" int mds_k_stem(const MdsFrames* frames, int n_images, const float* w, const float* bias, void* out, void* stream) {
+    if (!frames) return fail(MDS_ERR_INVALID, "null frames");
+    return launch_stem(*frames, n_images, w, bias, reinterpret_cast<__half*>(out), reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_conv3x3(const void* in, void* out, const void* w1, const float* b1, const void* w2, const float* b2,
+                             int n, int H, int W, int cin, int cmid, int stride, int cproj, int res, void* stream) {
+    return launch_conv3(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), reinterpret_cast<const __half*>(w1),
+                        b1, reinterpret_cast<const __half*>(w2), b2, n, H, W, cin, cmid, stride, cproj, res,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_gemm1x1(const void* A, const void* W, const float* bias, const void* res, const void* gate, void* C,
+                             int rows_per_img, int n_img, int N, int K, int act, void* stream) {
+    return launch_gemm(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(W), bias,
+                       reinterpret_cast<const __half*>(res), reinterpret_cast<const __half*>(gate),
+                       reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* sums, int n, int T, int H,
+                            int W, int C, int kt, int stride, void* stream) {
+    return launch_dw(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), w, bias, sums, n, T, H, W, C, kt,
+                     stride, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_se_fc(float* sums, const float* w1, const float* b1, const float* w2t, const float* b2, void* gate, int n,
+                           int C, int rd, float inv_count, void* stream) {
+    return launch_se(sums, w1, b1, w2t, b2, reinterpret_cast<__half*>(gate), n, C, rd, inv_count, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_gem(const void* x, float* feat, int b, int T, int P, int C, float p, float eps, void* stream) {
+    return launch_gem(reinterpret_cast<const __half*>(x), feat, b, T, P, C, p, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_linear(const float* feat, const float* w, const float* bias, float* out, int b, int F, int num_classes,
+                            int apply_sigmoid, void* stream) {
+    return launch_linear(feat, w, bias, out, b, F, num_classes, apply_sigmoid, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,142 @@
+// K5 (SE excitation MLP), K7 (GeM pooling + classifier) and the NCHW<->NHWC boundary converters.
+#pragma once
+#include "common.cuh"
+
+namespace mds {
+
+// gate[n][c] = sigmoid(W2 . SiLU(W1 . mean + b1) + b2), mean = sums / count.   One CTA per image.
+// Also clears sums[n][:] so the next depthwise layer can accumulate into the same buffer.
+struct SeParams {
+    float* sums;          // [n][C]
+    const float* w1;      // [rd][C]
+    const float* b1;      // [rd]
+    const float* w2t;     // [rd][C]  (conv_expand weight transposed)
+    const float* b2;      // [C]
+    __half* gate;         // [n][C]
+    int C, rd;
+    float inv_count;
+};
+
+__global__ void __launch_bounds__(256) se_fc_kernel(SeParams p) {
+    extern __shared__ float s_se[];
+    float* s_mean = s_se;            // [C]
+    float* s_hid = s_se + p.C;       // [rd]
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* sums = p.sums + (size_t)n * p.C;
+    for (int c = tid; c < p.C; c += 256) {
+        s_mean[c] = sums[c] * p.inv_count;
+        sums[c] = 0.f;
+    }
+    __syncthreads();
+    for (int j = warp; j < p.rd; j += 8) {
+        const float* w = p.w1 + (size_t)j * p.C;
+        float acc = 0.f;
+        for (int c = lane; c < p.C; c += 32) acc = fmaf(__ldg(w + c), s_mean[c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) s_hid[j] = silu_f(acc + __ldg(p.b1 + j));
+    }
+    __syncthreads();
+    for (int c = tid; c < p.C; c += 256) {
+        float acc = __ldg(p.b2 + c);
+        for (int j = 0; j < p.rd; ++j) acc = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], acc);
+        p.gate[(size_t)n * p.C + c] = __float2half_rn(sigmoid_f(acc));
+    }
+}
+
+// GeM (multidim_stacker.py:42-45) over the P = h*w positions of x[b][t][P][C]: feat[b][t*C + c].
+struct GemParams {
+    const __half* x;   // [b][T][P][C]
+    float* feat;       // [b][T*C]
+    int T, P, C;
+    float p, eps;
+};
+
+__global__ void __launch_bounds__(256) gem_kernel(GemParams g) {
+    __shared__ float s_part[8][260];
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int C8 = g.C >> 3;                 // threads along channels (8 ch each)
+    const int lanes_p = 256 / C8;            // position lanes
+    const int cg = tid % C8, pl = tid / C8;
+    const bool cube = (g.p == 3.0f);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const __half* base = g.x + (((size_t)b * g.T + t) * g.P) * g.C + cg * 8;
+    if (pl < lanes_p) {
+        for (int pos = pl; pos < g.P; pos += lanes_p) {
+            float v[8];
+            half8_to_float(ldg16(base + (size_t)pos * g.C), v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float x = fmaxf(v[i], g.eps);
+                acc[i] += cube ? x * x * x : powf(x, g.p);
+            }
+        }
+    }
+    // reduce over position lanes through smem (C <= 256, lanes_p <= 8)
+    if (pl < lanes_p) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[pl][cg * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < g.C) {
+        float s = 0.f;
+        for (int l = 0; l < lanes_p; ++l) s += s_part[l][tid];
+        float m = s / (float)g.P;
+        g.feat[(size_t)b * g.T * g.C + (size_t)t * g.C + tid] = cube ? cbrtf(m) : powf(m, 1.0f / g.p);
+    }
+}
+
+// logits[b][k] = feat[b] . W[k] + bias[k]  (nn.Linear, multidim_stacker.py:236); optional sigmoid (argus_models.py:26)
+__global__ void __launch_bounds__(256) linear_head_kernel(const float* feat, const float* w, const float* bias, float* out,
+                                                          int F, int num_classes, int apply_sigmoid) {
+    __shared__ float s_red[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = 0; k < num_classes; ++k) {
+        float acc = 0.f;
+        for (int i = tid; i < F; i += 256) acc = fmaf(feat[(size_t)b * F + i], __ldg(w + (size_t)k * F + i), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int i = 0; i < 8; ++i) s += s_red[i];
+            s += bias[k];
+            out[(size_t)b * num_classes + k] = apply_sigmoid ? 1.0f / (1.0f + expf(-s)) : s;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- boundary layout converters (the reference API is NCHW float32; the engine is NHWC fp16) ----------------
+// src [n][C][P] f32 -> dst [n][P][C] f16
+__global__ void __launch_bounds__(256) nchw32_to_nhwc16_kernel(const float* src, __half* dst, int C, int P) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, pp = p0 + tx;
+        tile[i][tx] = (c < C && pp < P) ? src[((size_t)n * C + c) * P + pp] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int pp = p0 + i, c = c0 + tx;
+        if (pp < P && c < C) dst[((size_t)n * P + pp) * C + c] = __float2half_rn(tile[tx][i]);
+    }
+}
+// src [n][P][C] f16 -> dst [n][C][P] f32
+__global__ void __launch_bounds__(256) nhwc16_to_nchw32_kernel(const __half* src, float* dst, int C, int P) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        int pp = p0 + i, c = c0 + tx;
+        tile[i][tx] = (pp < P && c < C) ? __half2float(src[((size_t)n * P + pp) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, pp = p0 + tx;
+        if (c < C && pp < P) dst[((size_t)n * C + c) * P + pp] = tile[tx][i];
+    }
+}
+
+}  // namespace mds

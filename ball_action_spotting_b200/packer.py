@@ -1,0 +1,91 @@
+"""state_dict (reference key names) -> packed tensors for libmds_b200: eval-mode BatchNorm folded into the
+preceding conv (scale into the weights, shift as a bias), fp16 K-major GEMM operands, fp32 depthwise / SE /
+classifier parameters.
+
+BN eps: 1e-3 for the timm ``tf_`` encoder, 1e-5 (nn.BatchNorm2d/3d default) for the reference-owned layers
+(multidim_stacker.py:59,178-185,198-205).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+
+ENC_EPS, REF_EPS = 1e-3, 1e-5
+# (kind, repeats, stride, expand, cout, has_se) — timm arch_def of tf_efficientnetv2_b0
+STAGES = [("cn", 1, 1, 1, 16, False), ("er", 2, 2, 4, 32, False), ("er", 2, 2, 4, 48, False),
+          ("ir", 3, 2, 4, 96, True), ("ir", 5, 1, 6, 112, True), ("ir", 8, 2, 6, 192, True)]
+
+
+def _fold(sd, wkey: str, bn: str, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    w = sd[wkey].detach().double().cpu()
+    gamma, beta = sd[bn + ".weight"].detach().double().cpu(), sd[bn + ".bias"].detach().double().cpu()
+    mean, var = sd[bn + ".running_mean"].detach().double().cpu(), sd[bn + ".running_var"].detach().double().cpu()
+    scale = gamma / torch.sqrt(var + eps)
+    w = w * scale.view(-1, *([1] * (w.ndim - 1)))
+    return w, beta - mean * scale
+
+
+def _h(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float16).contiguous()
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str, torch.Tensor]:
+    out: Dict[str, torch.Tensor] = {}
+    e = "conv2d_encoder."
+    w, b = _fold(sd, e + "conv_stem.weight", e + "bn1", ENC_EPS)           # [32][3][3][3]
+    out["stem.w"] = _f(w.permute(1, 2, 3, 0).reshape(27, 32))              # [(ci*3+r)*3+s][co]
+    out["stem.b"] = _f(b)
+
+    def conv3(name, wkey, bn):
+        w, b = _fold(sd, wkey, bn, ENC_EPS)                                # [co][ci][3][3]
+        out[name + ".w"] = _h(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))   # [co][(r*3+s)*ci + c]
+        out[name + ".b"] = _f(b)
+
+    def pw(name, wkey, bn, eps):
+        w, b = _fold(sd, wkey, bn, eps)
+        out[name + ".w"] = _h(w.reshape(w.shape[0], w.shape[1]))            # [co][ci]
+        out[name + ".b"] = _f(b)
+
+    def dw(name, wkey, bn, eps):
+        w, b = _fold(sd, wkey, bn, eps)                                    # [C][1][(kt)][3][3]
+        out[name + ".w"] = _f(w.reshape(w.shape[0], -1).t())                # [taps][C]
+        out[name + ".b"] = _f(b)
+
+    def se(name, prefix):
+        w1, w2 = sd[prefix + ".conv_reduce.weight"], sd[prefix + ".conv_expand.weight"]
+        out[name + ".w1"] = _f(w1.detach().cpu().reshape(w1.shape[0], w1.shape[1]))           # [rd][C]
+        out[name + ".b1"] = _f(sd[prefix + ".conv_reduce.bias"].detach().cpu())
+        out[name + ".w2t"] = _f(w2.detach().cpu().reshape(w2.shape[0], w2.shape[1]).t())      # [rd][C]
+        out[name + ".b2"] = _f(sd[prefix + ".conv_expand.bias"].detach().cpu())
+
+    for si, (kind, reps, _, _, _, _) in enumerate(STAGES):
+        for bi in range(reps):
+            p, n = f"{e}blocks.{si}.{bi}.", f"b{si}.{bi}"
+            if kind == "cn":
+                conv3(n + ".c3", p + "conv.weight", p + "bn1")
+            elif kind == "er":
+                conv3(n + ".c3", p + "conv_exp.weight", p + "bn1")
+                pw(n + ".pwl", p + "conv_pwl.weight", p + "bn2", ENC_EPS)
+            else:
+                pw(n + ".pw", p + "conv_pw.weight", p + "bn1", ENC_EPS)
+                dw(n + ".dw", p + "conv_dw.weight", p + "bn2", ENC_EPS)
+                se(n + ".se", p + "se")
+                pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3", ENC_EPS)
+
+    pw("proj2d", "conv2d_projection.0.weight", "conv2d_projection.1", REF_EPS)
+    for i in range(num_3d_blocks):
+        p, n = f"conv3d_encoder.{i}.", f"c3d.{i}"
+        pw(n + ".pw", p + "conv_pw.weight", p + "bn1.bn3d", REF_EPS)
+        dw(n + ".dw", p + "conv_dw.weight", p + "bn2.bn3d", REF_EPS)
+        se(n + ".se", p + "se")
+        pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3.bn3d", REF_EPS)
+    pw("proj3d", "conv3d_projection.0.weight", "conv3d_projection.1", REF_EPS)
+    out["gem.p"] = _f(sd["global_pool.p"].detach().cpu().reshape(1))
+    out["cls.w"] = _f(sd["classifier.weight"].detach().cpu())
+    out["cls.b"] = _f(sd["classifier.bias"].detach().cpu())
+    return out

@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — frame-stacks/sec of the MultiDimStacker FULL forward (15 x 1280 x 736 grayscale stack -> logits).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+One "step" = one pass of the hot path (stem -> encoder x5 -> 3D blocks -> GeM -> classifier) over one batch of B
+synthetic uint8 frame-stacks (BASELINE.json configs[1]: batch=4, fp16 storage / fp32 accumulate).  N>1: launched by
+torchrun, one rank per GPU, every rank runs its own batch (weak scaling) and the per-step logits are all-gathered over
+NCCL (the path's only exchange).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "frame-stacks/sec (15x1280x736)"
+UNIT = "frame-stacks/s"
+H, W, STORED_H, FRAMES = 736, 1280, 720, 15
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=4, help="frame-stacks per GPU per step (configs[1] = 4, configs[2] = 32)")
+    ap.add_argument("--chunk-images", type=int, default=0)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port (the reference is Python + un-vendored timm and cannot travel)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_forward_timer(steps: int, warmup: int):
+    import torch
+    from oracle import mds_oracle as O           # bench.py's cpu_baseline / --impl reference legs only
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.ModelConfig()
+    sd = O.make_state_dict(cfg, seed=1234)
+    x = torch.rand((1, FRAMES, H, W), generator=torch.Generator().manual_seed(0))
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.forward(sd, x, cfg)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    steps, warmup = min(steps, 5), min(warmup, 2)       # bounded: ~3 s per stack on 8 cores
+    times, cores = cpu_forward_timer(steps, warmup)
+    total = sum(times)
+    value = len(times) / total
+    sample = f"{len(times)} timed + {warmup} warm-up forwards of one (1,15,736,1280) fp32 stack, torch CPU, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "FULL forward, one 15x1280x736 stack per step (bounded sample of the B200 arm's workload)",
+                       "frames": FRAMES, "height": H, "width": W},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for ln in out.splitlines():
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # keep samples under load (upper half) for the median
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from ball_action_spotting_b200 import MultiDimStacker
+    from ball_action_spotting_b200 import accounting as acc
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device — the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, max(3, args.warmup)
+    T = FRAMES // 3
+
+    torch.manual_seed(1234)
+    net = MultiDimStacker("tf_efficientnetv2_b0.in1k", 2, num_frames=FRAMES, stack_size=3, num_3d_blocks=4,
+                          expansion_3d_ratio=3, se_reduce_3d_ratio=24, chunk_images=args.chunk_images)
+    net.init_random_(seed=1234)
+    net.to(dev).eval()
+    eng = net.engine(dev)
+
+    # synthetic uint8 frames; R rotating batches so that consecutive steps never re-read the same input from L2
+    bytes_in = B * FRAMES * STORED_H * W
+    R = max(2, -(-160_000_000 // bytes_in))                 # R * bytes_in > L2 (126 MB)
+    R = min(R, 8)
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    host = [torch.randint(0, 256, (B, FRAMES, STORED_H, W), dtype=torch.uint8, generator=g).pin_memory() for _ in range(min(R, 3))]
+    devb = [host[i % len(host)].to(dev, non_blocking=True) for i in range(R)]
+    logits = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * B, 2), dtype=torch.float32, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    def desc_of(t):
+        return eng.frames_desc(t, H, W, 3 * STORED_H * W, STORED_H * W)
+
+    def step_resident(i):
+        eng.forward(desc_of(devb[i % R]), B, out=logits)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logits)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for i in range(Wm):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.launch_count(reset=True)
+    ms = timed(step_resident, K)
+    launches = eng.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms / 1e3)
+
+    # ---- e2e: host (pinned) buffers -> H2D on a copy stream (double-buffered) -> forward -> D2H logits, every step ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty_like(devb[0]) for _ in range(2)]
+    host_out = torch.empty((B, 2), dtype=torch.float32).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        s = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[s])               # the forward that last read stage[s] has finished
+            stage[s].copy_(host[i % len(host)], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    state = {"next": 0}
+
+    def step_e2e(i):
+        s = i & 1
+        if state["next"] <= i:
+            upload(i); state["next"] = i + 1
+        if state["next"] <= i + 1:
+            upload(i + 1); state["next"] = i + 2             # prefetch the next batch while this one computes
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready[s])
+        eng.forward(desc_of(stage[s]), B, out=logits)
+        done[s].record(cur)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logits)
+        host_out.copy_(logits, non_blocking=True)
+
+    for ev in done:
+        ev.record(torch.cuda.current_stream(dev))
+    for i in range(2):
+        state["next"] = 0
+        step_e2e(0)
+        torch.cuda.synchronize()
+    state["next"] = 0
+    ms_e2e = timed(step_e2e, K)
+    e2e_value = world * B * K / (ms_e2e / 1e3)
+
+    # ---- per-kernel CUDA-event pass (same workload, same stream) for the roofline of the dominant kernel ----
+    roofline, by_kind = None, {}
+    if rank == 0:
+        torch.cuda.synchronize()
+        eng.profile_begin()
+        PK = min(K, 5)
+        for i in range(PK):
+            step_resident(i)
+        recs = eng.profile_end()
+        per_kind_ms = {}
+        for kind, tag, t in recs:
+            per_kind_ms[kind] = per_kind_ms.get(kind, 0.0) + t
+        tot = acc.per_stack_totals(H, W, STORED_H, T)
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            j = json.loads(pk.read_text())
+            peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "src": "measured"}
+        traffic = {}
+        tj = ROOT / "profiles" / "ncu_traffic.json"
+        if tj.exists():
+            traffic = json.loads(tj.read_text())
+        total_ms = sum(per_kind_ms.values())
+        for kind, kms in sorted(per_kind_ms.items(), key=lambda kv: -kv[1]):
+            name = acc.KINDS[kind]
+            a = tot.get(name, {"bytes": 0, "flops": 0, "launches": 1})
+            sec = kms / 1e3 / (PK * B)                    # seconds per stack spent in this kernel kind
+            gbs = a["bytes"] / sec / 1e9 if sec > 0 else 0.0
+            tfs = a["flops"] / sec / 1e12 if sec > 0 else 0.0
+            ai = a["flops"] / a["bytes"] if a["bytes"] else 0.0
+            tensor_bound = name == "conv3x3"              # AI 250-640 FLOP/B, above the ~215 FLOP/B ridge
+            entry = {"bound": "tensor" if tensor_bound else "hbm",
+                     "achieved": tfs if tensor_bound else gbs,
+                     "peak": peaks["bf16_tflops"] if tensor_bound else peaks["hbm_gbs"],
+                     "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                     "share_of_step": kms / total_ms if total_ms else 0.0,
+                     "ms_per_step": kms / PK, "algorithmic_bytes_per_stack": a["bytes"], "flops_per_stack": a["flops"],
+                     "gbs": gbs, "tflops": tfs, "traffic": traffic.get(name)}
+            entry["frac"] = entry["achieved"] / entry["peak"] if entry["peak"] else 0.0
+            by_kind[name] = entry
+        top = max(by_kind.items(), key=lambda kv: kv[1]["share_of_step"])
+        roofline = {"kernel": top[0], "bound": top[1]["bound"], "achieved": top[1]["achieved"], "peak": top[1]["peak"],
+                    "unit": top[1]["unit"], "frac": top[1]["frac"], "traffic": top[1]["traffic"],
+                    "peak_source": peaks["src"], "timing": f"per-launch CUDA events on the launching stream, {PK} steps"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_forward_timer(args.cpu_steps, 1)
+        cpu_baseline = {"value": len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{len(times)} timed + 1 warm-up forwards of one (1,15,736,1280) fp32 stack (oracle port, torch CPU)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
+                "data": "synthetic",
+                "config": {"workload": f"FULL MultiDimStacker forward, batch={B} stacks/GPU/step (BASELINE.json configs[1] is batch=4), "
+                                       "uint8 15x720x1280 frames -> pad 736 -> logits", "batch_per_gpu": B, "frames": FRAMES,
+                           "height": H, "width": W, "sharding": f"stacks x{world}, NCCL all-gather of logits" if world > 1 else "single GPU",
+                           "l2": f"{R} rotating input batches ({R * bytes_in / 1e6:.0f} MB) + >1 GB of intermediates per step: inputs larger than L2",
+                           "chunk_images": eng.cfg.chunk_images or 8},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": B * 2 * 4,
+                        "ms_per_step": ms_e2e / K},
+                "gpu_launches": launches,
+                "roofline": roofline, "roofline_by_kind": by_kind, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

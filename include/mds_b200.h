@@ -1,0 +1,126 @@
+/*
+ * mds_b200.h — C ABI of the B200-native MultiDimStacker forward path (libmds_b200.so).
+ *
+ * The reference (lRomul/ball-action-spotting) is pure Python/PyTorch and has no FFI for this path; the
+ * functions below are what a binding for the path would have to offer.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference repo).  All pointers are plain device pointers unless
+ * a parameter says "host"; no torch types cross this boundary.  Every function returns 0 on success and a
+ * negative MdsStatus on failure; mds_last_error() returns a thread-local message.  Launches are asynchronous
+ * on the caller's stream (the reference runs on the current stream without syncs, src/predictors.py:50).
+ * Ownership: the caller owns every input/output/workspace buffer; the handle owns only packed weights.
+ * A handle is bound to one device and is not thread-safe (the reference is single-threaded per device).
+ */
+#ifndef MDS_B200_H_
+#define MDS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct MdsHandle MdsHandle;
+
+typedef enum MdsStatus {
+    MDS_OK = 0,
+    MDS_ERR_INVALID = -1,   /* bad argument / unsupported shape (mirrors the asserts at multidim_stacker.py:155,212,223) */
+    MDS_ERR_WEIGHTS = -2,   /* missing / mis-sized tensor at commit (mirrors load_state_dict strictness) */
+    MDS_ERR_WORKSPACE = -3, /* workspace too small */
+    MDS_ERR_CUDA = -4       /* CUDA runtime error */
+} MdsStatus;
+
+/* kwargs of MultiDimStacker.__init__ that change shapes (src/models/multidim_stacker.py:138-153).
+ * model_name is fixed to tf_efficientnetv2_b0 (configs/ball_action/sampling_weights_001.py:31). */
+typedef struct MdsConfig {
+    int num_classes;
+    int num_frames;
+    int stack_size;          /* must be 3 */
+    int num_3d_blocks;
+    int num_3d_features;     /* must be 192 (== encoder feature width) */
+    int num_3d_stack_proj;   /* <= 256 */
+    int expansion_3d_ratio;
+    int se_reduce_3d_ratio;
+    int device;              /* CUDA ordinal */
+    int chunk_images;        /* images per pass through the 2D encoder (L2 blocking); 0 = default */
+} MdsConfig;
+
+/* Input frames for the 2D encoder: planar, `stack_size` consecutive planes are the channels of one image
+ * (multidim_stacker.py:214).  dtype 0: uint8 raw frames, zero-padded to (H, W) and divided by 255 inside the
+ * stem kernel (src/frames.py:7-31, PadNormalizeFramesProcessor); dtype 1: float32 already-normalised input
+ * (what MultiDimStacker.forward receives). */
+typedef struct MdsFrames {
+    const void* data;
+    int dtype;
+    long long img_stride;     /* elements between images */
+    long long plane_stride;   /* elements between the channel planes of one image */
+    int stored_h;             /* rows stored per plane (e.g. 720) */
+    int pad_top;              /* (H - stored_h) / 2, frames.py:19 */
+    int H, W;                 /* padded size, multiples of 32 */
+    int hflip;                /* 1: horizontal-flip TTA (kornia hflip, src/predictors.py:63) */
+} MdsFrames;
+
+const char* mds_last_error(void);
+
+/* argus.load_model -> BallActionModel(params) -> MultiDimStacker(**kwargs) (src/predictors.py:22,
+ * src/argus_models.py:17-21): create, then add every packed tensor, then commit. */
+int mds_create(const MdsConfig* cfg, MdsHandle** out);
+int mds_destroy(MdsHandle* h);
+/* nn.Module.load_state_dict: host_data is copied to the device. Names are listed in packer.py. */
+int mds_weights_add(MdsHandle* h, const char* name, const void* host_data, size_t nbytes);
+int mds_weights_commit(MdsHandle* h);
+
+size_t mds_workspace_bytes(const MdsHandle* h, int H, int W, int n_images, int n_stacks);
+
+/* MultiDimStacker.forward_2d (multidim_stacker.py:210-219): n_images 3-frame images -> feats fp16
+ * [n_images][H/32][W/32][192] (NHWC; the reference's (b, k, 192, h, w) with b*k = n_images). */
+int mds_forward_2d(MdsHandle* h, const MdsFrames* frames, int n_images, void* feats_out,
+                   void* ws, size_t ws_bytes, void* stream);
+/* MultiDimStacker.forward_3d (multidim_stacker.py:221-230): feats fp16 [b][T][fh][fw][192] -> out fp16
+ * [b][T][fh][fw][proj] (the reference's (b, proj*T, h, w) with channel = t*proj + c). */
+int mds_forward_3d(MdsHandle* h, const void* feats, int b, int fh, int fw, void* out, void* ws, size_t ws_bytes,
+                   void* stream);
+/* MultiDimStacker.forward_head (multidim_stacker.py:232-237) + optional nn.Sigmoid (src/argus_models.py:26). */
+int mds_forward_head(MdsHandle* h, const void* x, int b, int P, float* logits, int apply_sigmoid,
+                     void* ws, size_t ws_bytes, void* stream);
+/* MultiDimStacker.forward (multidim_stacker.py:239-243): b stacks of num_frames frames -> logits f32 [b][classes].
+ * frames->img_stride addresses image i = stack (i / T), triple (i % T). */
+int mds_forward(MdsHandle* h, const MdsFrames* frames, int b, float* logits, int apply_sigmoid,
+                void* ws, size_t ws_bytes, void* stream);
+
+/* Boundary layout converters (reference tensors are NCHW float32, the engine is NHWC fp16). */
+int mds_nchw32_to_nhwc16(const float* src, void* dst, int n, int C, int P, void* stream);
+int mds_nhwc16_to_nchw32(const void* src, float* dst, int n, int C, int P, void* stream);
+
+/* ---- per-kernel entry points (parity tests, ncu) ---- */
+int mds_k_stem(const MdsFrames* frames, int n_images, const float* w, const float* bias, void* out, void* stream);
+int mds_k_conv3x3(const void* in, void* out, const void* w1, const float* b1, const void* w2, const float* b2,
+                  int n, int H, int W, int cin, int cmid, int stride, int cproj, int res, void* stream);
+int mds_k_gemm1x1(const void* A, const void* W, const float* bias, const void* res, const void* gate, void* C,
+                  int rows_per_img, int n_img, int N, int K, int act, void* stream);
+int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* sums,
+                 int n, int T, int H, int W, int C, int kt, int stride, void* stream);
+int mds_k_se_fc(float* sums, const float* w1, const float* b1, const float* w2t, const float* b2, void* gate,
+                int n, int C, int rd, float inv_count, void* stream);
+int mds_k_gem(const void* x, float* feat, int b, int T, int P, int C, float p, float eps, void* stream);
+int mds_k_linear(const float* feat, const float* w, const float* bias, float* out, int b, int F, int num_classes,
+                 int apply_sigmoid, void* stream);
+
+/* Optional per-launch CUDA-event timing of this library's kernels (bench.py's live roofline measurement).
+ * begin: start recording (events on the launching stream); end: synchronise the events, return one record per
+ * launch (kind = MdsKernelKind, tag = layer id: 0 stem, 1..22 encoder blocks, 23 conv2d_projection, 101.. 3D
+ * blocks, 150 conv3d_projection, 200 head, -1 direct kernel call), stop recording. */
+typedef enum MdsKernelKind {
+    MDS_KIND_STEM = 0, MDS_KIND_CONV3X3 = 1, MDS_KIND_GEMM1X1 = 2, MDS_KIND_DWCONV2D = 3, MDS_KIND_DWCONV3D = 4,
+    MDS_KIND_SE_FC = 5, MDS_KIND_HEAD = 6
+} MdsKernelKind;
+int mds_profile_begin(void);
+int mds_profile_end(int* kinds, int* tags, float* ms, int capacity, int* count);
+
+/* number of kernels launched by this library in the calling thread since the last reset (bench "gpu_launches") */
+long long mds_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDS_B200_H_ */

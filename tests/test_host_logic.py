@@ -1,0 +1,91 @@
+"""CPU: host-side logic of the product package (no compute calls): reference API mirror, state-dict contract,
+BN folding, C-ABI symbol table."""
+import re
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mds_oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = (ROOT / "include" / "mds_b200.h").read_text()
+    declared = set(re.findall(r"\b(mds_[a-z0-9_]+)\s*\(", hdr))
+    from ball_action_spotting_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mds_last_error() is not None
+    assert lib.mds_launch_count(0) >= 0
+
+
+def test_state_dict_contract_matches_reference_keys(oracle_sd):
+    from ball_action_spotting_b200 import MultiDimStacker
+    net = MultiDimStacker("tf_efficientnetv2_b0.in1k", 2, num_frames=15, stack_size=3, num_3d_blocks=4,
+                          expansion_3d_ratio=3, se_reduce_3d_ratio=24, drop_rate=0.2, drop_path_rate=0.2)
+    mine = net.state_dict()
+    assert list(mine.keys()) == list(oracle_sd.keys())          # same keys, same order as the reference module
+    for k in mine:
+        assert mine[k].shape == oracle_sd[k].shape, k
+    net.load_state_dict(oracle_sd, strict=True)
+    assert net.num_stacks == 5 and net.num_features == 1280 and net.num_3d_features == 192
+    n_enc = sum(p.numel() for p in net.conv2d_encoder.parameters())
+    assert n_enc == 5_610_384
+
+
+def test_constructor_rejects_what_the_reference_rejects():
+    from ball_action_spotting_b200 import MultiDimStacker
+    with pytest.raises(AssertionError):
+        MultiDimStacker("tf_efficientnetv2_b0.in1k", 2, num_frames=16, stack_size=3)      # multidim_stacker.py:155
+    with pytest.raises(NotImplementedError):
+        MultiDimStacker("resnet18", 2)
+
+
+def test_no_cpu_fallback(oracle_sd):
+    from ball_action_spotting_b200 import MultiDimStacker
+    net = MultiDimStacker("tf_efficientnetv2_b0.in1k", 2, num_3d_blocks=4, expansion_3d_ratio=3).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 15, 64, 64))
+
+
+def test_bn_folding_reproduces_conv_bn(oracle_sd):
+    from ball_action_spotting_b200.packer import pack_state_dict
+    pk = pack_state_dict(oracle_sd, 4)
+    g = torch.Generator().manual_seed(0)
+    # dense 3x3 (blocks.1.1.conv_exp + bn1): packed [co][(r*3+s)*ci + c] fp16 / bias fp32
+    x = torch.randn(1, 32, 12, 12, generator=g)
+    p = "conv2d_encoder.blocks.1.1."
+    ref = O._bn(oracle_sd, p + "bn1", F.conv2d(x, oracle_sd[p + "conv_exp.weight"], padding=1), O.ENC_BN_EPS)
+    w = pk["b1.1.c3.w"].float().view(128, 3, 3, 32).permute(0, 3, 1, 2)
+    got = F.conv2d(x, w, pk["b1.1.c3.b"], padding=1)
+    assert (got - ref).abs().max() / ref.abs().max() < 1e-3      # fp16 weight rounding only
+    # depthwise 3x3x3 (conv3d_encoder.0.conv_dw + bn2): packed [taps][C] fp32 — exact up to fp32 rounding
+    x3 = torch.randn(1, 576, 3, 5, 5, generator=g)
+    p = "conv3d_encoder.0."
+    ref = O._bn(oracle_sd, p + "bn2.bn3d", F.conv3d(x3, oracle_sd[p + "conv_dw.weight"], padding=1, groups=576), O.REF_BN_EPS)
+    w = pk["c3d.0.dw.w"].t().reshape(576, 1, 3, 3, 3)
+    got = F.conv3d(x3, w, pk["c3d.0.dw.b"], padding=1, groups=576)
+    assert (got - ref).abs().max() / ref.abs().max() < 1e-5
+    # stem [27][32]
+    xs = torch.rand(1, 3, 16, 16, generator=g)
+    ref = O._bn(oracle_sd, "conv2d_encoder.bn1", O._conv_same(xs, oracle_sd["conv2d_encoder.conv_stem.weight"], 2), O.ENC_BN_EPS)
+    w = pk["stem.w"].view(3, 3, 3, 32).permute(3, 0, 1, 2)
+    got = F.conv2d(F.pad(xs, (0, 1, 0, 1)), w, pk["stem.b"], stride=2)
+    assert (got - ref).abs().max() / ref.abs().max() < 1e-5
+    assert pk["b5.7.se.w2t"].shape == (48, 1152) and pk["cls.w"].shape == (2, 1280)
+
+
+def test_host_mirrors_equal_oracle_restatements():
+    from ball_action_spotting_b200 import StackIndexesGenerator, get_frames_processor
+    for size, step in [(15, 2), (33, 2), (5, 1)]:
+        gen = StackIndexesGenerator(size, step)
+        for i in (-2, 0, 40, 99):
+            assert gen.make_stack_indexes(i) == O.make_stack_indexes(i, size, step)
+            assert gen.clip_index(i, 100, 1) == O.clip_index(i, 100, size, step, 1)
+    u8 = torch.randint(0, 256, (2, 3, 720, 1280), dtype=torch.uint8, generator=torch.Generator().manual_seed(1))
+    proc = get_frames_processor("pad_normalize", dict(size=(1280, 736), pad_mode="constant", fill_value=0))
+    assert torch.equal(proc(u8), O.pad_normalize(u8, (1280, 736)))

@@ -1,0 +1,235 @@
+"""GPU: per-kernel parity through the C-ABI.  Each kernel is fed the tensors the oracle's layer would see (rounded to
+the fp16 storage format), and its output is compared with the oracle's fp32 torch op on the same inputs.
+Tolerance (north_star): max|got - ref| / max|ref| <= 1e-3."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mds_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+DEV = "cuda:0"
+
+
+def rel(got, ref):
+    return ((got.float().cpu() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-12)).item()
+
+
+def gen(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+def h16(t):
+    return t.to(torch.float16)
+
+
+def ok(rc, lib):
+    assert rc == 0, lib.mds_last_error().decode()
+
+
+def nhwc(t):  # (n, C, H, W) -> (n, H, W, C) contiguous
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize("dtype,hflip", [("u8", 0), ("u8", 1), ("f32", 0)])
+def test_stem(lib, dtype, hflip):
+    from ball_action_spotting_b200._lib import MdsFrames
+    n, H, W = 2, 96, 160
+    w = torch.randn(32, 3, 3, 3, generator=gen(1)) * 0.3
+    b = torch.randn(32, generator=gen(2)) * 0.1
+    if dtype == "u8":
+        raw = torch.randint(0, 256, (n, 3, 80, W), dtype=torch.uint8, generator=gen(3))
+        x = O.pad_normalize(raw, (W, H))
+        dt, stored_h = 0, 80
+    else:
+        raw = torch.rand((n, 3, H, W), generator=gen(3))
+        x = raw
+        dt, stored_h = 1, H
+    if hflip:
+        x = x.flip(-1)
+    ref = F.silu(F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2))
+    d_raw = raw.to(DEV)
+    d_w = w.permute(1, 2, 3, 0).reshape(27, 32).contiguous().to(DEV)
+    d_b = b.to(DEV)
+    out = torch.empty((n, H // 2, W // 2, 32), dtype=torch.float16, device=DEV)
+    fr = MdsFrames(d_raw.data_ptr(), dt, 3 * stored_h * W, stored_h * W, stored_h, (H - stored_h) // 2, H, W, hflip)
+    ok(lib.mds_k_stem(C.byref(fr), n, d_w.data_ptr(), d_b.data_ptr(), out.data_ptr(), None), lib)
+    torch.cuda.synchronize()
+    assert rel(nchw(out), ref) <= TOL
+
+
+@pytest.mark.parametrize("cin,cmid,stride,cproj,res", [(32, 16, 1, 0, 0), (16, 64, 2, 32, 0), (32, 128, 1, 32, 1),
+                                                       (32, 128, 2, 48, 0), (48, 192, 1, 48, 1)])
+@pytest.mark.parametrize("hw", [(24, 40), (46, 34)])
+def test_conv3x3(lib, cin, cmid, stride, cproj, res, hw):
+    n, (H, W) = 2, hw
+    x = h16(torch.randn(n, cin, H, W, generator=gen(1)))
+    w1 = h16(torch.randn(cmid, cin, 3, 3, generator=gen(2)) * (2.0 / (9 * cin)) ** 0.5)
+    b1 = torch.randn(cmid, generator=gen(3)) * 0.1
+    xf = x.float()
+    y = F.conv2d(xf, w1.float(), b1, padding=1) if stride == 1 else F.conv2d(F.pad(xf, (0, 1, 0, 1)), w1.float(), b1, stride=2)
+    y = F.silu(y)
+    w2 = b2 = None
+    if cproj:
+        w2 = h16(torch.randn(cproj, cmid, generator=gen(4)) * (1.0 / cmid) ** 0.5)
+        b2 = torch.randn(cproj, generator=gen(5)) * 0.1
+        # the kernel feeds the SiLU output to the projection as fp16 MMA operands
+        y = F.conv2d(h16(y).float(), w2.float()[:, :, None, None], b2)
+        if res:
+            y = y + xf
+    ref = y
+    cout = cproj or cmid
+    Ho, Wo = ref.shape[-2:]
+    d_x = nhwc(x).to(DEV)
+    d_w1 = w1.permute(0, 2, 3, 1).reshape(cmid, -1).contiguous().to(DEV)
+    d_b1 = b1.to(DEV)
+    d_w2 = w2.contiguous().to(DEV) if cproj else None
+    d_b2 = b2.to(DEV) if cproj else None
+    out = torch.zeros((n, Ho, Wo, cout), dtype=torch.float16, device=DEV)
+    ok(lib.mds_k_conv3x3(d_x.data_ptr(), out.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(),
+                         d_w2.data_ptr() if cproj else None, d_b2.data_ptr() if cproj else None,
+                         n, H, W, cin, cmid, stride, cproj, res, None), lib)
+    torch.cuda.synchronize()
+    assert rel(nchw(out), ref) <= TOL
+
+
+GEMM_CASES = [  # (N, K, gated, res, act)
+    (192, 48, 0, 0, 1), (96, 192, 1, 0, 0), (384, 96, 0, 0, 1), (96, 384, 1, 1, 0), (576, 96, 0, 0, 1),
+    (112, 576, 1, 0, 0), (672, 112, 0, 0, 1), (112, 672, 1, 1, 0), (192, 672, 1, 0, 0), (1152, 192, 0, 0, 1),
+    (192, 1152, 1, 1, 0), (192, 192, 0, 0, 1), (576, 192, 0, 0, 1), (192, 576, 1, 1, 0), (256, 192, 0, 0, 1),
+    (64, 32, 0, 0, 0)]
+
+
+@pytest.mark.parametrize("N,K,gated,res,act", GEMM_CASES)
+def test_gemm1x1(lib, N, K, gated, res, act):
+    rows, n_img = 150, 3
+    M = rows * n_img
+    A = h16(torch.randn(M, K, generator=gen(1)))
+    Wt = h16(torch.randn(N, K, generator=gen(2)) * (1.0 / K) ** 0.5)
+    bias = torch.randn(N, generator=gen(3)) * 0.1
+    a = A.float()
+    g = None
+    if gated:
+        g = h16(torch.rand(n_img, K, generator=gen(4)))
+        # the kernel multiplies the fp16 A fragments by the fp16 gate (one fp16 rounding)
+        a = h16(a.view(n_img, rows, K) * g.float()[:, None, :]).float().view(M, K)
+    y = a @ Wt.float().t() + bias
+    if act:
+        y = F.silu(y)
+    r = None
+    if res:
+        r = h16(torch.randn(M, N, generator=gen(5)))
+        y = y + r.float()
+    d = lambda t: None if t is None else t.contiguous().to(DEV)
+    dA, dW, db, dr, dg = d(A), d(Wt), d(bias), d(r), d(g)
+    out = torch.zeros((M, N), dtype=torch.float16, device=DEV)
+    p = lambda t: None if t is None else t.data_ptr()
+    ok(lib.mds_k_gemm1x1(p(dA), p(dW), p(db), p(dr), p(dg), out.data_ptr(), rows, n_img, N, K, act, None), lib)
+    torch.cuda.synchronize()
+    assert rel(out, y) <= TOL
+
+
+@pytest.mark.parametrize("C_,stride", [(192, 2), (384, 1), (576, 1), (672, 1), (672, 2), (1152, 1)])
+def test_dwconv2d_and_se_sums(lib, C_, stride):
+    n, H, W = 3, 22, 18
+    x = h16(torch.randn(n, C_, H, W, generator=gen(1)))
+    w = torch.randn(C_, 1, 3, 3, generator=gen(2)) * 0.3
+    b = torch.randn(C_, generator=gen(3)) * 0.1
+    xf = x.float()
+    y = F.conv2d(xf, w, b, padding=1, groups=C_) if stride == 1 else F.conv2d(F.pad(xf, (0, 1, 0, 1)), w, b, stride=2, groups=C_)
+    y = F.silu(y)
+    d_x = nhwc(x).to(DEV)
+    d_w = w.reshape(C_, 9).t().contiguous().to(DEV)
+    d_b = b.to(DEV)
+    Ho, Wo = y.shape[-2:]
+    out = torch.zeros((n, Ho, Wo, C_), dtype=torch.float16, device=DEV)
+    sums = torch.zeros((n, C_), dtype=torch.float32, device=DEV)
+    ok(lib.mds_k_dwconv(d_x.data_ptr(), out.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), sums.data_ptr(),
+                        n, 1, H, W, C_, 1, stride, None), lib)
+    torch.cuda.synchronize()
+    assert rel(nchw(out), y) <= TOL
+    assert rel(sums, y.sum((2, 3))) <= 1e-4          # fp32 squeeze sums of the un-rounded SiLU output
+
+
+@pytest.mark.parametrize("T", [5, 11])
+def test_dwconv3d_and_se_sums(lib, T):
+    n, C_, H, W = 2, 576, 7, 9
+    x = h16(torch.randn(n, C_, T, H, W, generator=gen(1)))
+    w = torch.randn(C_, 1, 3, 3, 3, generator=gen(2)) * 0.2
+    b = torch.randn(C_, generator=gen(3)) * 0.1
+    y = F.silu(F.conv3d(x.float(), w, b, padding=1, groups=C_))
+    d_x = x.permute(0, 2, 3, 4, 1).contiguous().to(DEV)          # (n, T, H, W, C)
+    d_w = w.reshape(C_, 27).t().contiguous().to(DEV)
+    d_b = b.to(DEV)
+    out = torch.zeros((n, T, H, W, C_), dtype=torch.float16, device=DEV)
+    sums = torch.zeros((n, C_), dtype=torch.float32, device=DEV)
+    ok(lib.mds_k_dwconv(d_x.data_ptr(), out.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), sums.data_ptr(),
+                        n, T, H, W, C_, 3, 1, None), lib)
+    torch.cuda.synchronize()
+    assert rel(out.permute(0, 4, 1, 2, 3), y) <= TOL
+    assert rel(sums, y.sum((2, 3, 4))) <= 1e-4
+
+
+@pytest.mark.parametrize("C_,rd", [(672, 28), (576, 24), (1152, 48), (192, 12)])
+def test_se_fc(lib, C_, rd):
+    n, count = 3, 920
+    sums = torch.randn(n, C_, generator=gen(1)) * count * 0.3
+    w1 = torch.randn(rd, C_, generator=gen(2)) * (2.0 / rd) ** 0.5 * 0.2
+    b1 = torch.randn(rd, generator=gen(3)) * 0.1
+    w2 = torch.randn(C_, rd, generator=gen(4)) * (2.0 / C_) ** 0.5
+    b2 = torch.randn(C_, generator=gen(5)) * 0.1
+    mean = sums / count
+    ref = torch.sigmoid(F.silu(mean @ w1.t() + b1) @ w2.t() + b2)
+    d_s, d_w1, d_b1, d_w2t, d_b2 = sums.to(DEV), w1.to(DEV), b1.to(DEV), w2.t().contiguous().to(DEV), b2.to(DEV)
+    gate = torch.zeros((n, C_), dtype=torch.float16, device=DEV)
+    ok(lib.mds_k_se_fc(d_s.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(), d_w2t.data_ptr(), d_b2.data_ptr(),
+                       gate.data_ptr(), n, C_, rd, 1.0 / count, None), lib)
+    torch.cuda.synchronize()
+    assert rel(gate, ref) <= TOL
+    assert float(d_s.abs().max()) == 0.0             # the kernel hands the buffer back zeroed
+
+
+@pytest.mark.parametrize("p", [3.0, 2.5])
+def test_gem_and_linear(lib, p):
+    b, T, P, C_ = 2, 5, 35, 256
+    x = h16(torch.randn(b, T, P, C_, generator=gen(1)) * 2)
+    xr = x.float().permute(0, 1, 3, 2).reshape(b, T * C_, P, 1)          # reference layout (b, T*C, h, w)
+    feat_ref = O.gem(xr, torch.tensor([p]))
+    w = torch.randn(2, T * C_, generator=gen(2)) * 0.05
+    bias = torch.randn(2, generator=gen(3)) * 0.1
+    ref = F.linear(feat_ref, w, bias)
+    d_x, d_w, d_b = x.to(DEV), w.to(DEV), bias.to(DEV)
+    feat = torch.zeros((b, T * C_), dtype=torch.float32, device=DEV)
+    out = torch.zeros((b, 2), dtype=torch.float32, device=DEV)
+    ok(lib.mds_k_gem(d_x.data_ptr(), feat.data_ptr(), b, T, P, C_, p, 1e-6, None), lib)
+    ok(lib.mds_k_linear(feat.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), out.data_ptr(), b, T * C_, 2, 0, None), lib)
+    torch.cuda.synchronize()
+    assert rel(feat, feat_ref) <= 1e-5
+    assert rel(out, ref) <= 1e-5
+
+
+def test_layout_converters_round_trip(lib):
+    n, C_, P = 3, 192, 77
+    x = torch.randn(n, C_, P, generator=gen(1))
+    d_x = x.to(DEV)
+    y = torch.zeros((n, P, C_), dtype=torch.float16, device=DEV)
+    z = torch.zeros((n, C_, P), dtype=torch.float32, device=DEV)
+    ok(lib.mds_nchw32_to_nhwc16(d_x.data_ptr(), y.data_ptr(), n, C_, P, None), lib)
+    ok(lib.mds_nhwc16_to_nchw32(y.data_ptr(), z.data_ptr(), n, C_, P, None), lib)
+    torch.cuda.synchronize()
+    assert torch.equal(y.cpu(), h16(x).permute(0, 2, 1))
+    assert torch.equal(z.cpu(), h16(x).float())
+
+
+def test_errors_are_reported_not_swallowed(lib):
+    rc = lib.mds_k_gemm1x1(None, None, None, None, None, None, 10, 1, 100, 30, 0, None)
+    assert rc != 0 and b"multiples of 16" in lib.mds_last_error()
+    rc = lib.mds_k_conv3x3(None, None, None, None, None, None, 1, 8, 8, 7, 7, 1, 0, 0, None)
+    assert rc != 0 and b"unsupported" in lib.mds_last_error()
