@@ -1,10 +1,14 @@
 // K4/K6: depthwise 3x3 (2D, stride 1/2, TF-SAME) and 3x3x3 (3D, pad 1) convolution + folded BN + SiLU, NHWC fp16,
 // with the SE squeeze (per-image channel sums over the output, fp32) produced in the same pass
 // (timm InvertedResidual conv_dw/bn2/se; multidim_stacker.py:110-114,86).
-// HBM-bound: each thread owns 4 channels (8-byte loads, a warp covers 256 contiguous bytes of one pixel) and one
-// output column, and slides down the rows; every loaded input row is scattered into the three output rows it
-// contributes to, so the only live state is 3 accumulators x 4 channels.  The next row is prefetched before the
-// current one is consumed.
+//
+// HBM-bound streaming kernel.  A CTA owns (image, [out plane t], 40 output columns, 64-channel slab, row chunk) and
+// streams the input rows it needs through a ring of shared-memory stages filled by cp.async (16 B per request,
+// zero-fill for the padding halo, rows beyond the image and channel tails), several rows ahead of the math, so the
+// bytes in flight per SM do not depend on registers or occupancy.  Warp w computes output columns [5w, 5w+5); lane l
+// owns channels (2l, 2l+1) of the slab as one packed f32x2, so every shared-memory read is a conflict-free LDS.32,
+// every global store is a 128-byte line per pixel, and the MACs are packed FFMA2 (fma.rn.f32x2).  Each input row is
+// scattered into the (up to) three output rows it contributes to; the window never lives in registers.
 #pragma once
 #include "common.cuh"
 
@@ -17,203 +21,171 @@ struct DwParams {
     const float* bias;   // [C]
     float* sums;         // [n][C]  += sum over (T,Ho,Wo) of the fp32 SiLU output
     int n, T, H, W, C, Ho, Wo;
-    int rows_per_chunk, chunks;
+    int rows_per_chunk, chunks, xtiles, slabs;
 };
 
-__device__ __forceinline__ void half4_to_float(const uint2& v, float (&f)[4]) {
-    float2 a = unpack_half2(v.x), b = unpack_half2(v.y);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
-}
+constexpr int kDwCS = 64;      // channels per slab (lane = 2 channels)
+constexpr int kDwPXW = 5;      // output columns per warp
+constexpr int kDwTWX = 40;     // output columns per CTA (8 warps)
 
-__device__ __forceinline__ void dw_block_sums(float (&lsum)[4], int c0, bool active, float* s_sum, float* gsum, int C) {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s_sum[i] = 0.f;
-    __syncthreads();
-    if (active) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) atomicAdd(&s_sum[c0 + i], lsum[i]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        float v = s_sum[i];
-        if (v != 0.f) atomicAdd(&gsum[i], v);
-    }
-}
+template <int KT, int STRIDE>
+struct DwCfg {
+    static constexpr int IW = (STRIDE == 1) ? kDwTWX + 2 : 2 * kDwTWX + 1;   // input columns per row tile
+    static constexpr int NV = (STRIDE == 1) ? kDwPXW + 2 : 2 * kDwPXW + 1;   // input columns per warp strip
+    static constexpr int ROW_HALVES = IW * kDwCS;
+    static constexpr int STAGE_HALVES = KT * ROW_HALVES;
+    static constexpr int NST = (KT == 3) ? 4 : (STRIDE == 2 ? 6 : 8);
+    static constexpr size_t SMEM = (size_t)NST * STAGE_HALVES * 2 + 8 * kDwCS * sizeof(float);
+};
 
-// ---- 2D: weights in registers -------------------------------------------------------------------------------
-template <int STRIDE>
-__global__ void __launch_bounds__(256) dwconv2d_kernel(DwParams p) {
-    extern __shared__ float s_sum[];
-    const int C4 = p.C >> 2;
-    const int f = blockIdx.x * 256 + threadIdx.x;
-    const bool active = f < p.Wo * C4;
-    const int xo = active ? f / C4 : 0;
-    const int c0 = active ? (f - xo * C4) * 4 : 0;
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+template <int KT, int STRIDE>
+__global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
+    using Cfg = DwCfg<KT, STRIDE>;
+    static_assert(KT == 1 || STRIDE == 1, "3D depthwise is stride 1");
+    extern __shared__ __align__(16) unsigned char dw_smem[];
+    __half* s_ring = reinterpret_cast<__half*>(dw_smem);
+    float* s_part = reinterpret_cast<float*>(dw_smem + (size_t)Cfg::NST * Cfg::STAGE_HALVES * 2);   // [8][64]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int xt = blockIdx.x % p.xtiles, slab = blockIdx.x / p.xtiles;
+    const int t = blockIdx.y / p.chunks, chunk = blockIdx.y - t * p.chunks;
     const int n = blockIdx.z;
-    const int yo0 = blockIdx.y * p.rows_per_chunk;
-    const int yo1 = min(p.Ho, yo0 + p.rows_per_chunk);
-    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const int yo0 = chunk * p.rows_per_chunk, yo1 = min(p.Ho, yo0 + p.rows_per_chunk);
+    const int xo0 = xt * kDwTWX;
+    const int c_slab = slab * kDwCS;
+    const int c = c_slab + 2 * lane;
+    const bool c_ok = c < p.C;
+    const int c_ld = c_ok ? c : 0;
 
-    if (active && yo0 < yo1) {
-        float w[9][4], b[4];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)t * p.C + c0));
-            w[t][0] = v.x; w[t][1] = v.y; w[t][2] = v.z; w[t][3] = v.w;
-        }
-        {
-            float4 v = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
-            b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
-        }
-        const __half* in = p.in + (size_t)n * p.H * p.W * p.C + c0;
-        __half* out = p.out + (size_t)n * p.Ho * p.Wo * p.C + (size_t)xo * p.C + c0;
-        // input columns of the three taps; TF-SAME: stride 1 -> pad 1 both sides, stride 2 (even W) -> pad right only
-        const int xi0 = xo * STRIDE - (STRIDE == 1 ? 1 : 0);
-        bool xok[3];
-#pragma unroll
-        for (int s = 0; s < 3; ++s) xok[s] = (xi0 + s >= 0) && (xi0 + s < p.W);
+    // input rows consumed by this chunk and the first input column of the tile (TF-SAME: pad 1 / pad right-bottom only)
+    const int yi0 = (STRIDE == 1) ? yo0 - 1 : 2 * yo0;
+    const int NR = (STRIDE == 1) ? (yo1 - yo0) + 2 : 2 * (yo1 - yo0) + 1;
+    const int xi0 = (STRIDE == 1) ? xo0 - 1 : 2 * xo0;
 
-        auto load_row = [&](int yi, uint2 (&v)[3]) {
-            const bool yok = (yi >= 0) && (yi < p.H);
-            const __half* row = in + ((size_t)yi * p.W + xi0) * p.C;
+    const size_t plane = (size_t)p.H * p.W * p.C;
+    const __half* in_n = p.in + (size_t)n * p.T * plane;
+
+    auto issue = [&](int k) {
+        __half* st = s_ring + (k % Cfg::NST) * Cfg::STAGE_HALVES;
+        const int yi = yi0 + k;
+        const bool yok = (yi >= 0) && (yi < p.H);
+        for (int idx = tid; idx < KT * Cfg::IW * 8; idx += 256) {
+            const int pl = idx / (Cfg::IW * 8);
+            const int rem = idx - pl * (Cfg::IW * 8);
+            const int px = rem >> 3, c16 = rem & 7;
+            const int xi = xi0 + px;
+            const int ti = (KT == 3) ? t + pl - 1 : t;
+            const int cc = c_slab + c16 * 8;
+            const bool ok = yok && (xi >= 0) && (xi < p.W) && (ti >= 0) && (ti < p.T) && (cc < p.C);
+            const __half* src = ok ? in_n + (size_t)ti * plane + ((size_t)yi * p.W + xi) * p.C + cc : p.in;
+            cp_async16(st + pl * Cfg::ROW_HALVES + px * kDwCS + c16 * 8, src, ok ? 16 : 0);
+        }
+    };
+
+    // per-thread weights: KT*9 taps x 2 channels
+    float2 w[KT * 9];
 #pragma unroll
-            for (int s = 0; s < 3; ++s)
-                v[s] = (yok && xok[s]) ? __ldg(reinterpret_cast<const uint2*>(row + (size_t)s * p.C)) : make_uint2(0u, 0u);
-        };
-        auto emit = [&](int yo, float (&a)[4]) {
-            float o[4];
+    for (int i = 0; i < KT * 9; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)i * p.C + c_ld));
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + c_ld));
+
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { o[i] = silu_f(a[i] + b[i]); lsum[i] += o[i]; }
-            uint2 v; v.x = pack_half2(o[0], o[1]); v.y = pack_half2(o[2], o[3]);
-            *reinterpret_cast<uint2*>(out + (size_t)yo * p.Wo * p.C) = v;
-        };
+    for (int k = 0; k < Cfg::NST - 1; ++k) {
+        if (k < NR) issue(k);
+        cp_async_commit();
+    }
+
+    float2 lsum = make_float2(0.f, 0.f);
+    float2 a0[kDwPXW], a1[kDwPXW], a2[kDwPXW];
+#pragma unroll
+    for (int j = 0; j < kDwPXW; ++j) a0[j] = a1[j] = a2[j] = make_float2(0.f, 0.f);
+
+    const int xw = xo0 + warp * kDwPXW;               // first output column of this warp
+    const int px_base = (STRIDE == 1) ? warp * kDwPXW : 2 * warp * kDwPXW;
+    __half* out_base = p.out + ((size_t)n * p.T + t) * (size_t)p.Ho * p.Wo * p.C + c;
+
+    auto emit = [&](int yo, const float2 (&acc)[kDwPXW]) {
+        __half* row = out_base + ((size_t)yo * p.Wo + xw) * p.C;
+#pragma unroll
+        for (int j = 0; j < kDwPXW; ++j) {
+            if (c_ok && xw + j < p.Wo) {
+                const float ox = silu_f(acc[j].x + bias.x), oy = silu_f(acc[j].y + bias.y);
+                lsum.x += ox; lsum.y += oy;
+                *reinterpret_cast<uint32_t*>(row + (size_t)j * p.C) = pack_half2(ox, oy);
+            }
+        }
+    };
+
+    for (int k = 0; k < NR; ++k) {
+        cp_async_wait<Cfg::NST - 2>();
+        __syncthreads();
+        if (k + Cfg::NST - 1 < NR) issue(k + Cfg::NST - 1);
+        cp_async_commit();
+
+        const __half* st = s_ring + (k % Cfg::NST) * Cfg::STAGE_HALVES + px_base * kDwCS + 2 * lane;
+        const int yi = yi0 + k;
 
         if constexpr (STRIDE == 1) {
             // input row yi feeds out rows yi+1 (kernel row 0), yi (row 1), yi-1 (row 2)
-            float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4];   // a0: out yi-1, a1: out yi, a2: out yi+1
-            uint2 cur[3], nxt[3];
-            load_row(yo0 - 1, cur);
-            for (int yi = yo0 - 1; yi <= yo1; ++yi) {
-                if (yi < yo1) load_row(yi + 1, nxt);
-                float v[3][4];
 #pragma unroll
-                for (int s = 0; s < 3; ++s) half4_to_float(cur[s], v[s]);
+            for (int j = 0; j < kDwPXW; ++j) a2[j] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    a0[i] = fmaf(w[6][i], v[0][i], fmaf(w[7][i], v[1][i], fmaf(w[8][i], v[2][i], a0[i])));
-                    a1[i] = fmaf(w[3][i], v[0][i], fmaf(w[4][i], v[1][i], fmaf(w[5][i], v[2][i], a1[i])));
-                    a2[i] = fmaf(w[0][i], v[0][i], fmaf(w[1][i], v[1][i], w[2][i] * v[2][i]));
-                }
-                if (yi - 1 >= yo0) emit(yi - 1, a0);
+            for (int dt = 0; dt < KT; ++dt) {
+                float2 v[Cfg::NV];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { a0[i] = a1[i]; a1[i] = a2[i]; }
+                for (int i = 0; i < Cfg::NV; ++i)
+                    v[i] = __half22float2(*reinterpret_cast<const __half2*>(st + dt * Cfg::ROW_HALVES + i * kDwCS));
 #pragma unroll
-                for (int s = 0; s < 3; ++s) cur[s] = nxt[s];
-            }
-        } else {
-            // out row yo reads input rows 2yo (kernel row 0), 2yo+1, 2yo+2; row 2yo+2 is also kernel row 0 of yo+1
-            float acc[4];
-            uint2 r0[3], ra[3], rb[3];
-            load_row(2 * yo0, r0);
-            {
-                float v[3][4];
-#pragma unroll
-                for (int s = 0; s < 3; ++s) half4_to_float(r0[s], v[s]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = fmaf(w[0][i], v[0][i], fmaf(w[1][i], v[1][i], w[2][i] * v[2][i]));
-            }
-            load_row(2 * yo0 + 1, ra);
-            load_row(2 * yo0 + 2, rb);
-            for (int yo = yo0; yo < yo1; ++yo) {
-                uint2 na[3], nb[3];
-                if (yo + 1 < yo1) { load_row(2 * yo + 3, na); load_row(2 * yo + 4, nb); }
-                float va[3][4], vb[3][4], nacc[4];
-#pragma unroll
-                for (int s = 0; s < 3; ++s) { half4_to_float(ra[s], va[s]); half4_to_float(rb[s], vb[s]); }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc[i] = fmaf(w[3][i], va[0][i], fmaf(w[4][i], va[1][i], fmaf(w[5][i], va[2][i], acc[i])));
-                    acc[i] = fmaf(w[6][i], vb[0][i], fmaf(w[7][i], vb[1][i], fmaf(w[8][i], vb[2][i], acc[i])));
-                    nacc[i] = fmaf(w[0][i], vb[0][i], fmaf(w[1][i], vb[1][i], w[2][i] * vb[2][i]));
-                }
-                emit(yo, acc);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = nacc[i];
-#pragma unroll
-                for (int s = 0; s < 3; ++s) { ra[s] = na[s]; rb[s] = nb[s]; }
-            }
-        }
-    }
-    dw_block_sums(lsum, c0, active, s_sum, p.sums + (size_t)n * p.C, p.C);
-}
-
-// ---- 3D (3x3x3, stride 1, pad 1): weights streamed through L1 -------------------------------------------------
-__global__ void __launch_bounds__(256) dwconv3d_kernel(DwParams p) {
-    extern __shared__ float s_sum[];
-    const int C4 = p.C >> 2;
-    const int f = blockIdx.x * 256 + threadIdx.x;
-    const bool active = f < p.Wo * C4;
-    const int xo = active ? f / C4 : 0;
-    const int c0 = active ? (f - xo * C4) * 4 : 0;
-    const int n = blockIdx.z;
-    const int t = blockIdx.y / p.chunks;
-    const int chunk = blockIdx.y - t * p.chunks;
-    const int yo0 = chunk * p.rows_per_chunk;
-    const int yo1 = min(p.Ho, yo0 + p.rows_per_chunk);
-    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
-
-    if (active && yo0 < yo1) {
-        float b[4];
-        {
-            float4 v = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
-            b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
-        }
-        const size_t plane = (size_t)p.H * p.W * p.C;
-        const __half* in = p.in + (size_t)n * p.T * plane + c0;
-        __half* out = p.out + ((size_t)n * p.T + t) * plane + (size_t)xo * p.C + c0;
-        const float* wp = p.w + c0;
-        bool xok[3];
-#pragma unroll
-        for (int s = 0; s < 3; ++s) xok[s] = (xo - 1 + s >= 0) && (xo - 1 + s < p.W);
-
-        float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
-        for (int yi = yo0 - 1; yi <= yo1; ++yi) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a2[i] = 0.f;
-            if (yi >= 0 && yi < p.H) {
-#pragma unroll
-                for (int dt = 0; dt < 3; ++dt) {
-                    const int ti = t + dt - 1;
-                    if (ti < 0 || ti >= p.T) continue;
-                    const __half* row = in + (size_t)ti * plane + ((size_t)yi * p.W + (xo - 1)) * p.C;
+                for (int j = 0; j < kDwPXW; ++j)
 #pragma unroll
                     for (int s = 0; s < 3; ++s) {
-                        if (!xok[s]) continue;
-                        float v[4];
-                        half4_to_float(__ldg(reinterpret_cast<const uint2*>(row + (size_t)s * p.C)), v);
-                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)((dt * 3 + 0) * 3 + s) * p.C));
-                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)((dt * 3 + 1) * 3 + s) * p.C));
-                        const float4 w2 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)((dt * 3 + 2) * 3 + s) * p.C));
-                        a2[0] = fmaf(w0.x, v[0], a2[0]); a2[1] = fmaf(w0.y, v[1], a2[1]);
-                        a2[2] = fmaf(w0.z, v[2], a2[2]); a2[3] = fmaf(w0.w, v[3], a2[3]);
-                        a1[0] = fmaf(w1.x, v[0], a1[0]); a1[1] = fmaf(w1.y, v[1], a1[1]);
-                        a1[2] = fmaf(w1.z, v[2], a1[2]); a1[3] = fmaf(w1.w, v[3], a1[3]);
-                        a0[0] = fmaf(w2.x, v[0], a0[0]); a0[1] = fmaf(w2.y, v[1], a0[1]);
-                        a0[2] = fmaf(w2.z, v[2], a0[2]); a0[3] = fmaf(w2.w, v[3], a0[3]);
+                        a2[j] = ffma2(w[dt * 9 + 0 + s], v[j + s], a2[j]);
+                        a1[j] = ffma2(w[dt * 9 + 3 + s], v[j + s], a1[j]);
+                        a0[j] = ffma2(w[dt * 9 + 6 + s], v[j + s], a0[j]);
+                    }
+            }
+            if (yi - 1 >= yo0) emit(yi - 1, a0);        // yi - 1 < yo1 always holds (yi <= yo1)
+#pragma unroll
+            for (int j = 0; j < kDwPXW; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; }
+        } else {
+            // stride 2: even input row 2yo is kernel row 0 of out yo and kernel row 2 of out yo-1; odd row 2yo+1 is row 1
+            float2 v[Cfg::NV];
+#pragma unroll
+            for (int i = 0; i < Cfg::NV; ++i) v[i] = __half22float2(*reinterpret_cast<const __half2*>(st + i * kDwCS));
+            if ((k & 1) == 0) {       // yi = 2*yo0 + k is even
+#pragma unroll
+                for (int j = 0; j < kDwPXW; ++j) {
+                    a2[j] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        a1[j] = ffma2(w[6 + s], v[2 * j + s], a1[j]);     // closes out row (yi/2 - 1)
+                        a2[j] = ffma2(w[0 + s], v[2 * j + s], a2[j]);     // opens out row yi/2
                     }
                 }
-            }
-            if (yi - 1 >= yo0) {
-                float o[4];
+                if (k > 0) emit((yi >> 1) - 1, a1);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { o[i] = silu_f(a0[i] + b[i]); lsum[i] += o[i]; }
-                uint2 v; v.x = pack_half2(o[0], o[1]); v.y = pack_half2(o[2], o[3]);
-                *reinterpret_cast<uint2*>(out + (size_t)(yi - 1) * p.Wo * p.C) = v;
-            }
+                for (int j = 0; j < kDwPXW; ++j) a1[j] = a2[j];
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a0[i] = a1[i]; a1[i] = a2[i]; }
+                for (int j = 0; j < kDwPXW; ++j)
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) a1[j] = ffma2(w[3 + s], v[2 * j + s], a1[j]);
+            }
         }
     }
-    dw_block_sums(lsum, c0, active, s_sum, p.sums + (size_t)n * p.C, p.C);
+    cp_async_wait<0>();
+
+    // ---- SE squeeze: reduce the 8 warps' partial sums, one global atomic per channel per CTA ----
+    s_part[warp * kDwCS + 2 * lane] = lsum.x;
+    s_part[warp * kDwCS + 2 * lane + 1] = lsum.y;
+    __syncthreads();
+    if (tid < kDwCS && c_slab + tid < p.C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += s_part[i * kDwCS + tid];
+        atomicAdd(p.sums + (size_t)n * p.C + c_slab + tid, s);
+    }
 }
 
 }  // namespace mds

@@ -111,7 +111,8 @@ static int num_sms() {
 // kernel launchers
 // --------------------------------------------------------------------------------------------------------------
 static int launch_stem(const MdsFrames& f, int n, const float* w, const float* bias, __half* out, cudaStream_t st) {
-    if (f.H % 2 || f.W % 2 || f.H <= 0 || f.W <= 0) return fail(MDS_ERR_INVALID, "stem: H, W must be even");
+    if (f.H % 2 || f.W % 4 || f.H <= 0 || f.W <= 0) return fail(MDS_ERR_INVALID, "stem: H must be even, W a multiple of 4");
+    if (f.img_stride % 4 || f.plane_stride % 4) return fail(MDS_ERR_INVALID, "stem: image / plane strides must be multiples of 4 elements");
     if (n <= 0) return MDS_OK;
     StemParams p;
     p.in = f.data; p.img_stride = f.img_stride; p.plane_stride = f.plane_stride;
@@ -212,50 +213,62 @@ static int launch_gemm(const __half* A, const __half* W, const float* bias, cons
     return fail(MDS_ERR_INVALID, "gemm1x1: N=%d is not a multiple of 128/112/96/64", N);
 }
 
+template <int KT, int STRIDE>
+static int launch_dw_t(const DwParams& p, dim3 grid, cudaStream_t st) {
+    using Cfg = DwCfg<KT, STRIDE>;
+    auto kern = dwconv_kernel<KT, STRIDE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    ProfScope ps(KT == 1 ? MDS_KIND_DWCONV2D : MDS_KIND_DWCONV3D, st);
+    kern<<<grid, 256, Cfg::SMEM, st>>>(p);
+    LAUNCH_CHECK("dwconv");
+    return MDS_OK;
+}
+
 static int launch_dw(const __half* in, __half* out, const float* w, const float* bias, float* sums, int n, int T,
                      int H, int W, int C, int kt, int stride, cudaStream_t st) {
-    if (C % 4 || C > 4096) return fail(MDS_ERR_INVALID, "dwconv: C must be a multiple of 4");
+    if (C % 8 || C > 4096) return fail(MDS_ERR_INVALID, "dwconv: C must be a multiple of 8");
     if (!((kt == 1 && (stride == 1 || stride == 2)) || (kt == 3 && stride == 1)))
         return fail(MDS_ERR_INVALID, "dwconv: unsupported kt=%d stride=%d", kt, stride);
     if (kt == 1 && T != 1) return fail(MDS_ERR_INVALID, "dwconv 2D: T must be 1");
     if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "dwconv: stride-2 input must be even");
     if (n <= 0) return MDS_OK;
+    if (n > 65535) return fail(MDS_ERR_INVALID, "dwconv: n too large");
     DwParams p;
     p.in = in; p.out = out; p.w = w; p.bias = bias; p.sums = sums;
     p.n = n; p.T = T; p.H = H; p.W = W; p.C = C;
     p.Ho = H / stride; p.Wo = W / stride;
-    const int bx = (p.Wo * (C / 4) + 255) / 256;
-    // enough CTAs to fill the machine a few times over: split rows when the batch is small
+    p.xtiles = (p.Wo + kDwTWX - 1) / kDwTWX;
+    p.slabs = (C + kDwCS - 1) / kDwCS;
+    // enough CTAs to fill the machine a few times over: split rows when the batch is small (halo rows are re-read)
     int chunks = 1;
-    const long long base = (long long)bx * n * T;
-    const long long want = (long long)num_sms() * 8;
+    const long long base = (long long)p.xtiles * p.slabs * n * T;
+    const long long want = (long long)num_sms() * 6;
     if (base < want) {
         chunks = (int)((want + base - 1) / base);
-        if (chunks > p.Ho / 4) chunks = p.Ho / 4 > 0 ? p.Ho / 4 : 1;
+        const int max_chunks = p.Ho / 6 > 0 ? p.Ho / 6 : 1;
+        if (chunks > max_chunks) chunks = max_chunks;
     }
     p.rows_per_chunk = (p.Ho + chunks - 1) / chunks;
     p.chunks = (p.Ho + p.rows_per_chunk - 1) / p.rows_per_chunk;
-    dim3 grid(bx, p.chunks * T, n);
-    const size_t smem = (size_t)C * sizeof(float);
-    ProfScope ps(kt == 1 ? MDS_KIND_DWCONV2D : MDS_KIND_DWCONV3D, st);
-    if (kt == 1) {
-        if (stride == 1) dwconv2d_kernel<1><<<grid, 256, smem, st>>>(p);
-        else dwconv2d_kernel<2><<<grid, 256, smem, st>>>(p);
-    } else {
-        dwconv3d_kernel<<<grid, 256, smem, st>>>(p);
-    }
-    LAUNCH_CHECK("dwconv");
-    return MDS_OK;
+    if ((long long)p.chunks * T > 65535) return fail(MDS_ERR_INVALID, "dwconv: grid.y too large");
+    dim3 grid(p.xtiles * p.slabs, p.chunks * T, n);
+    if (kt == 3) return launch_dw_t<3, 1>(p, grid, st);
+    if (stride == 1) return launch_dw_t<1, 1>(p, grid, st);
+    return launch_dw_t<1, 2>(p, grid, st);
 }
 
 static int launch_se(float* sums, const float* w1, const float* b1, const float* w2t, const float* b2, __half* gate,
                      int n, int C, int rd, float inv_count, cudaStream_t st) {
     if (n <= 0) return MDS_OK;
-    if (C > 4096 || rd > 256) return fail(MDS_ERR_INVALID, "se_fc: C/rd too large");
+    if (C > 4096 || rd > 256 || C % 4) return fail(MDS_ERR_INVALID, "se_fc: C must be a multiple of 4, C <= 4096, rd <= 256");
     SeParams p;
     p.sums = sums; p.w1 = w1; p.b1 = b1; p.w2t = w2t; p.b2 = b2; p.gate = gate; p.C = C; p.rd = rd; p.inv_count = inv_count;
     ProfScope ps(MDS_KIND_SE_FC, st);
-    se_fc_kernel<<<n, 256, (size_t)(C + rd) * sizeof(float), st>>>(p);
+    se_fc_kernel<<<n, kSeThreads, (size_t)(C + rd) * sizeof(float), st>>>(p);
     LAUNCH_CHECK("se_fc");
     return MDS_OK;
 }

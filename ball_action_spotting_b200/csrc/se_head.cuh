@@ -17,29 +17,42 @@ struct SeParams {
     float inv_count;
 };
 
-__global__ void __launch_bounds__(256) se_fc_kernel(SeParams p) {
+constexpr int kSeThreads = 1024;
+__global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
     extern __shared__ float s_se[];
     float* s_mean = s_se;            // [C]
     float* s_hid = s_se + p.C;       // [rd]
     const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* sums = p.sums + (size_t)n * p.C;
-    for (int c = tid; c < p.C; c += 256) {
+    for (int c = tid; c < p.C; c += kSeThreads) {
         s_mean[c] = sums[c] * p.inv_count;
         sums[c] = 0.f;
     }
     __syncthreads();
-    for (int j = warp; j < p.rd; j += 8) {
-        const float* w = p.w1 + (size_t)j * p.C;
-        float acc = 0.f;
-        for (int c = lane; c < p.C; c += 32) acc = fmaf(__ldg(w + c), s_mean[c], acc);
-        acc = warp_sum(acc);
+    // squeeze FC: one hidden unit per warp pass, 4 independent partial sums per lane so the loads overlap
+    for (int j = warp; j < p.rd; j += kSeThreads / 32) {
+        const float4* w = reinterpret_cast<const float4*>(p.w1 + (size_t)j * p.C);
+        const float4* m = reinterpret_cast<const float4*>(s_mean);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int c = lane; c < p.C / 4; c += 32) {
+            const float4 wv = __ldg(w + c), mv = m[c];
+            a0 = fmaf(wv.x, mv.x, a0); a1 = fmaf(wv.y, mv.y, a1); a2 = fmaf(wv.z, mv.z, a2); a3 = fmaf(wv.w, mv.w, a3);
+        }
+        const float acc = warp_sum((a0 + a1) + (a2 + a3));
         if (lane == 0) s_hid[j] = silu_f(acc + __ldg(p.b1 + j));
     }
     __syncthreads();
-    for (int c = tid; c < p.C; c += 256) {
-        float acc = __ldg(p.b2 + c);
-        for (int j = 0; j < p.rd; ++j) acc = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], acc);
-        p.gate[(size_t)n * p.C + c] = __float2half_rn(sigmoid_f(acc));
+    for (int c = tid; c < p.C; c += kSeThreads) {
+        float a0 = __ldg(p.b2 + c), a1 = 0.f;
+        int j = 0;
+#pragma unroll 4
+        for (; j + 1 < p.rd; j += 2) {
+            a0 = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], a0);
+            a1 = fmaf(__ldg(p.w2t + (size_t)(j + 1) * p.C + c), s_hid[j + 1], a1);
+        }
+        if (j < p.rd) a0 = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], a0);
+        p.gate[(size_t)n * p.C + c] = __float2half_rn(sigmoid_f(a0 + a1));
     }
 }
 

@@ -2,6 +2,8 @@
 // (timm conv_stem 3x3 s2 TF-SAME + bn1 + SiLU).  Reads planar uint8 (or already-normalised float) frames,
 // treats `stack_size`=3 frames as the input channels (multidim_stacker.py:214), writes NHWC fp16 [n][H/2][W/2][32].
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mds {
@@ -21,11 +23,12 @@ struct StemParams {
 };
 
 constexpr int kStemTW = 32, kStemTH = 8, kStemC = 32;
-constexpr int kStemIW = 2 * kStemTW + 1, kStemIH = 2 * kStemTH + 1, kStemIWP = kStemIW + 1;
+constexpr int kStemIW = 2 * kStemTW + 1, kStemIH = 2 * kStemTH + 1;
+constexpr int kStemWPR = (kStemIW + 3) / 4, kStemIWP = kStemWPR * 4;   // tile rows are loaded as 4-element words
 
 template <typename IN_T>
 __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
-    __shared__ float s_in[3][kStemIH][kStemIWP];
+    __shared__ __align__(16) float s_in[3][kStemIH][kStemIWP];
     __shared__ __align__(16) float s_w[27 * kStemC];
     __shared__ float s_b[kStemC];
 
@@ -37,18 +40,44 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
     if (tid < kStemC) s_b[tid] = p.bias[tid];
 
     const IN_T* img = reinterpret_cast<const IN_T*>(p.in) + (long long)n * p.img_stride;
-    for (int i = tid; i < 3 * kStemIH * kStemIW; i += 256) {
-        int ci = i / (kStemIH * kStemIW);
-        int rem = i - ci * (kStemIH * kStemIW);
-        int iy = rem / kStemIW, ix = rem - iy * kStemIW;
-        int y = 2 * oy0 + iy, x = 2 * ox0 + ix;   // TF-SAME on even input: pad bottom/right only
-        float v = 0.f;
-        int ys = y - p.pad_top;
-        if (y < p.H && x < p.W && ys >= 0 && ys < p.stored_h) {
-            int xs = p.hflip ? (p.W - 1 - x) : x;
-            v = static_cast<float>(img[ci * p.plane_stride + (long long)ys * p.W + xs]) / p.divisor;
+    // Tile = 3 planes x 17 rows x 17 words of 4 pixels.  All of a thread's loads are issued before any is consumed.
+    constexpr int kItems = 3 * kStemIH * kStemWPR, kIters = (kItems + 255) / 256;
+    using Word = typename std::conditional<sizeof(IN_T) == 1, uint32_t, float4>::type;
+    Word vals[kIters];
+    bool okv[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+        const int i = tid + it * 256;
+        const int ci = i / (kStemIH * kStemWPR);
+        const int rem = i - ci * (kStemIH * kStemWPR);
+        const int iy = rem / kStemWPR, wd = rem - iy * kStemWPR;
+        const int y = 2 * oy0 + iy, x = 2 * ox0 + 4 * wd;   // TF-SAME on even input: pad bottom/right only
+        const int ys = y - p.pad_top;
+        okv[it] = (i < kItems) && (y < p.H) && (x < p.W) && (ys >= 0) && (ys < p.stored_h);
+        if (okv[it]) {
+            const int xs = p.hflip ? (p.W - 4 - x) : x;
+            vals[it] = __ldg(reinterpret_cast<const Word*>(img + ci * p.plane_stride + (long long)ys * p.W + xs));
         }
-        s_in[ci][iy][ix] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+        const int i = tid + it * 256;
+        if (i >= kItems) continue;
+        const int ci = i / (kStemIH * kStemWPR);
+        const int rem = i - ci * (kStemIH * kStemWPR);
+        const int iy = rem / kStemWPR, wd = rem - iy * kStemWPR;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (okv[it]) {
+            if constexpr (sizeof(IN_T) == 1) {
+                const uint32_t u = vals[it];
+                v = make_float4((float)(u & 0xffu), (float)((u >> 8) & 0xffu), (float)((u >> 16) & 0xffu), (float)(u >> 24));
+            } else {
+                v = vals[it];
+            }
+            if (p.hflip) v = make_float4(v.w, v.z, v.y, v.x);
+            v.x /= p.divisor; v.y /= p.divisor; v.z /= p.divisor; v.w /= p.divisor;
+        }
+        *reinterpret_cast<float4*>(&s_in[ci][iy][4 * wd]) = v;
     }
     __syncthreads();
 
@@ -59,7 +88,7 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
         float acc[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = s_b[cg * 8 + c];
-#pragma unroll
+#pragma unroll 1
         for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
             for (int r = 0; r < 3; ++r)

@@ -1,18 +1,45 @@
 """GPU: end-to-end parity of the drop-in module / predictor against the CPU fp32 oracle on identical inputs.
 
-Tolerance (north_star): logits within 1e-3 relative (max|got-ref| / max|ref|), sigmoid probabilities within 1e-3.
-The intermediate API tensors (forward_2d / forward_3d) are stored in fp16 by design (BASELINE.json config 2); a
-random-weight network amplifies each fp16 rounding ~1.1x per layer (DESIGN.md "Numerics"), so they are held to
-INTERMEDIATE_TOL, and every kernel is separately held to 1e-3 on oracle inputs in test_kernels_gpu.py."""
+Tolerance (north_star): logits within 1e-3 relative (max|got-ref| / max|ref|) and sigmoid probabilities within 1e-3
+on 15 x 1280 x 736 frame-stacks (BASELINE.json configs[0]) — NORTH_STAR_TOL, used unscaled by every full-size test.
+
+The engine stores activations in fp16 with fp32 accumulation (BASELINE.json configs[1]).  Each stored tensor carries
+an independent rounding noise of ~2.8e-4 relative; GeM pooling averages it over the P = (H/32)*(W/32) feature-map
+positions, so the logit noise falls as 1/sqrt(P).  The reduced-size tests below (kept small so the CPU oracle runs in
+seconds) therefore use tol_for(H, W) = 1e-3 * sqrt(920 / P): the SAME per-element accuracy requirement, expressed at
+their P (920 = 23*40 positions at 1280x736).  The intermediate API tensors (forward_2d / forward_3d) have no pooling
+and a random-weight network amplifies each rounding ~1.1x per layer (DESIGN.md "Numerics"), so they are held to
+INTERMEDIATE_TOL; every kernel is separately held to 1e-3 on oracle inputs in test_kernels_gpu.py.
+Every measured error is appended to gpurun_out/parity_report.jsonl."""
+import json
+import math
+from pathlib import Path
+
 import pytest
 import torch
 
 from oracle import mds_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-3
+NORTH_STAR_TOL = 1e-3
 INTERMEDIATE_TOL = 1e-2
 DEV = "cuda:0"
+REPORT = Path(__file__).resolve().parents[1] / "gpurun_out" / "parity_report.jsonl"
+
+
+def tol_for(h, w):
+    P = (h // 32) * (w // 32)
+    return NORTH_STAR_TOL * max(1.0, math.sqrt(920.0 / P))
+
+
+def record(name, err, tol):
+    try:
+        REPORT.parent.mkdir(exist_ok=True)
+        with REPORT.open("a") as f:
+            f.write(json.dumps({"test": name, "err": err, "tol": tol}) + "\n")
+    except OSError:
+        pass
+    return err
 
 
 def rel(got, ref):
@@ -43,10 +70,10 @@ def test_forward_small_batch2(net5, oracle_sd):
     xd = x.to(DEV)
     got = net5(xd)
     assert got.shape == (2, 2) and got.dtype == torch.float32
-    e = rel(got, ref)
-    print("logits", got.cpu().tolist(), ref.tolist(), "rel", e)
+    TOL = tol_for(96, 160)
+    e = record("small_b2.logits", rel(got, ref), TOL)
     assert e <= TOL
-    assert (torch.sigmoid(got.cpu()) - torch.sigmoid(ref)).abs().max().item() <= TOL
+    assert record("small_b2.probs", (torch.sigmoid(got.cpu()) - torch.sigmoid(ref)).abs().max().item(), TOL) <= TOL
     f2 = net5.forward_2d(xd)
     assert f2.shape == f2r.shape == (2, 5, 192, 3, 5)
     e2 = rel(f2, f2r)
@@ -54,12 +81,13 @@ def test_forward_small_batch2(net5, oracle_sd):
     assert f3.shape == f3r.shape == (2, 1280, 3, 5)
     e3 = rel(f3, f3r)
     lg = net5.forward_head(f3)
-    print("forward_2d rel", e2, "forward_3d rel", e3, "staged logits rel", rel(lg, ref))
+    record("small_b2.forward_2d", e2, INTERMEDIATE_TOL)
+    record("small_b2.forward_3d", e3, INTERMEDIATE_TOL)
     assert e2 <= INTERMEDIATE_TOL and e3 <= INTERMEDIATE_TOL
-    assert rel(lg, ref) <= 2 * TOL      # staged path adds two fp16 boundary conversions
+    assert record("small_b2.staged_logits", rel(lg, ref), 2 * TOL) <= 2 * TOL      # two extra fp16 boundary conversions
     # forward_3d / forward_head on the ORACLE's own intermediates (no accumulated drift)
-    assert rel(net5.forward_3d(f2r.to(DEV)), f3r) <= INTERMEDIATE_TOL
-    assert rel(net5.forward_head(f3r.to(DEV)), ref) <= TOL
+    assert record("small_b2.forward_3d_from_oracle_f2", rel(net5.forward_3d(f2r.to(DEV)), f3r), INTERMEDIATE_TOL) <= INTERMEDIATE_TOL
+    assert record("small_b2.head_from_oracle_f3", rel(net5.forward_head(f3r.to(DEV)), ref), NORTH_STAR_TOL) <= NORTH_STAR_TOL
 
 
 def test_forward_uint8_frames_fused_pad_normalize(net5, oracle_sd):
@@ -68,7 +96,7 @@ def test_forward_uint8_frames_fused_pad_normalize(net5, oracle_sd):
     with torch.no_grad():
         ref = O.forward(oracle_sd, O.pad_normalize(u8, (160, 96)), cfg)
     got = net5(u8.to(DEV))
-    assert rel(got, ref) <= TOL
+    assert record("small_u8.logits", rel(got, ref), tol_for(96, 160)) <= tol_for(96, 160)
 
 
 def test_forward_full_size_config1(net5, oracle_sd):
@@ -78,10 +106,19 @@ def test_forward_full_size_config1(net5, oracle_sd):
     with torch.no_grad():
         ref = O.forward(oracle_sd, x, cfg)
     got = net5(x.to(DEV))
-    e = rel(got, ref)
-    print("full-size logits", got.cpu().tolist(), ref.tolist(), "rel", e)
-    assert e <= TOL
-    assert (torch.sigmoid(got.cpu()) - torch.sigmoid(ref)).abs().max().item() <= TOL
+    assert record("full_config1.logits", rel(got, ref), NORTH_STAR_TOL) <= NORTH_STAR_TOL
+    assert record("full_config1.probs", (torch.sigmoid(got.cpu()) - torch.sigmoid(ref)).abs().max().item(), NORTH_STAR_TOL) <= NORTH_STAR_TOL
+
+
+def test_forward_full_size_uint8_batch2(net5, oracle_sd):
+    """Two raw 15 x 720 x 1280 uint8 stacks (what the predictor sees): fused pad 720->736 + /255, full-size parity."""
+    cfg = O.ModelConfig()
+    u8 = torch.randint(0, 256, (2, 15, 720, 1280), dtype=torch.uint8, generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        ref = O.forward(oracle_sd, O.pad_normalize(u8, (1280, 736)), cfg)
+    got = net5(u8.to(DEV))
+    assert record("full_u8_b2.logits", rel(got, ref), NORTH_STAR_TOL) <= NORTH_STAR_TOL
+    assert record("full_u8_b2.probs", (torch.sigmoid(got.cpu()) - torch.sigmoid(ref)).abs().max().item(), NORTH_STAR_TOL) <= NORTH_STAR_TOL
 
 
 def test_forward_33_frames_T11():
@@ -91,7 +128,7 @@ def test_forward_33_frames_T11():
     x = torch.rand((1, 33, 96, 160), generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
         ref = O.forward(sd, x, cfg)
-    assert rel(net(x.to(DEV)), ref) <= TOL
+    assert record("small_T11.logits", rel(net(x.to(DEV)), ref), tol_for(96, 160)) <= tol_for(96, 160)
 
 
 def test_batch_is_per_sample_deterministic(net5):
@@ -141,7 +178,37 @@ def test_streaming_predictor_matches_reference_semantics(tmp_path, oracle_sd, tt
         if ref is not None:
             n_pred += 1
             assert got.shape == (2,)
-            assert (got.cpu() - ref).abs().max().item() <= TOL, (i, got.cpu().tolist(), ref.tolist())
+            e = record(f"predictor_tta{int(tta)}.probs[{i}]", (got.cpu() - ref).abs().max().item(), tol_for(96, 160))
+            assert e <= tol_for(96, 160), (i, got.cpu().tolist(), ref.tolist())
     assert n_pred == 36 - 28
     pred.reset_buffers()
     assert pred.predict(frames[0].to(DEV), 0)[0] is None
+
+
+def test_streaming_predictor_full_size_tta(tmp_path, oracle_sd):
+    """Full-size (720x1280 frames, TTA on) streaming parity at the north-star tolerance: 31 frames -> 3 predictions."""
+    from ball_action_spotting_b200 import MultiDimStackerPredictor
+    cfg = O.ModelConfig()
+    params = {"nn_module": ("multidim_stacker", dict(model_name="tf_efficientnetv2_b0.in1k", num_classes=2, num_frames=15,
+                                                     stack_size=3, index_2d_features=4, pretrained=False, num_3d_blocks=4,
+                                                     num_3d_features=192, expansion_3d_ratio=3, se_reduce_3d_ratio=24,
+                                                     num_3d_stack_proj=256, drop_rate=0.2, drop_path_rate=0.2, act_layer="silu")),
+              "frames_processor": ("pad_normalize", {"size": (1280, 736), "pad_mode": "constant", "fill_value": 0}),
+              "frame_stack_size": 15, "frame_stack_step": 2, "device": ["cuda:0"]}
+    path = tmp_path / "model-001-0.500000.pth"
+    torch.save({"model_name": "BallActionModel", "params": params, "nn_state_dict": oracle_sd}, path)
+    pred = MultiDimStackerPredictor(path, device=DEV, tta=True)
+    orc = O.StreamingPredictorOracle(oracle_sd, cfg, 2, (1280, 736), tta=True)
+    frames = torch.randint(0, 256, (31, 720, 1280), dtype=torch.uint8, generator=torch.Generator().manual_seed(21))
+    n_pred = 0
+    for i in range(31):
+        got, gi = pred.predict(frames[i].to(DEV), i)
+        if i < 28:
+            assert got is None and gi == i - 14
+            orc.frames[i] = O.pad_normalize(frames[i][None, None], (1280, 736))[0, 0]   # buffer only, skip the oracle forward
+            continue
+        ref, ri = orc.predict(frames[i], i)
+        assert gi == ri and got is not None and ref is not None
+        n_pred += 1
+        assert record(f"predictor_full_tta.probs[{i}]", (got.cpu() - ref).abs().max().item(), NORTH_STAR_TOL) <= NORTH_STAR_TOL
+    assert n_pred == 3
