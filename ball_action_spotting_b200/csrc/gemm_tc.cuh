@@ -1,0 +1,265 @@
+// K3 on the 5th-gen tensor cores: persistent, warp-specialised 1x1-conv GEMM for sm_100a.
+//   C[m][n] = act( sum_k A[m][k] * W[n][k] + bias[n] )            A = NHWC fp16 activations, W = [cout][cin] fp16
+// These GEMMs are HBM-bound (AI < 200 FLOP/B) and, for the expand convs, output-dominated, so the design goal is
+// to stream A once, write C once and keep the bias+SiLU epilogue off the critical path:
+//   * a CTA owns a 128-row A tile (K <= 192 -> at most three 128x64 blocks, resident in smem, double-buffered
+//     across row tiles) and sweeps ALL N tiles of it, streaming only W blocks (L2-resident) through a TMA ring;
+//   * warp 0 / lane 0 : TMA producer (cp.async.bulk.tensor 2D, 128-byte swizzle, OOB rows / K tail zero-filled
+//     by the TMA unit, mbarrier expect_tx);
+//   * warp 1          : TMEM allocator; lane 0 issues tcgen05.mma (M=128, N=BN, K=16, fp16 -> fp32 in TMEM) and
+//     tcgen05.commit to release smem and to publish finished accumulators;
+//   * warps 2-17      : epilogue — tcgen05.ld 16 accumulator columns per request, bias + SiLU in fp32, one rounding
+//     to fp16, one 32-byte (full sector) st.global.v8 per request; no smem staging;
+//   * two accumulators (2*BN TMEM columns): the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mds {
+
+struct TcGemmParams {
+    const float* bias;    // [N]
+    __half* C;            // [M][N]
+    long long M;
+    int N, K, BN;
+    int act;
+    int m_tiles, n_tiles;
+    int stages;           // W ring depth
+    int tmem_cols;        // power of two >= 2*BN
+};
+
+constexpr int kTcBM = 128, kTcBK = 64, kTcMaxKB = 3;
+constexpr int kTcEpiWarps = 16;
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
+constexpr int kTcABytes = kTcBM * kTcBK * 2;          // 16 KB per K block
+
+__host__ __device__ inline int tc_stages(int BN) { return BN > 192 ? 3 : 4; }
+__host__ __device__ inline size_t tc_smem_bytes(int BN) {
+    return 1024 /*align slack*/ + (size_t)2 * kTcMaxKB * kTcABytes + (size_t)tc_stages(BN) * BN * 128 + 256 /*barriers*/;
+}
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug must surface as a trap (-> CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 (fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzled operand tile: rows are 128 B, 8-row groups are 1024 B apart (cute::UMMA::SmemDescriptor:
+// start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled K-major, 1), SBO>>4 [32,46) = 64, version [46,48) = 1,
+// layout [61,64) = 2 (SWIZZLE_128B)).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b_format F16 (0), K-major A and B, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t tc_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcGemmParams p) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    // 1024-byte alignment is required by the 128-byte swizzle atoms
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* s_a = smem;                                           // [2][kTcMaxKB][16 KB]
+    unsigned char* s_b = smem + (size_t)2 * kTcMaxKB * kTcABytes;        // [stages][BN * 128 B]
+    const int b_bytes = p.BN * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + (size_t)p.stages * b_bytes);
+    uint64_t* b_full = bars;                  // [4]
+    uint64_t* b_empty = bars + 4;             // [4]
+    uint64_t* a_full = bars + 8;              // [2]
+    uint64_t* a_empty = bars + 10;            // [2]
+    uint64_t* acc_full = bars + 12;           // [2]
+    uint64_t* acc_empty = bars + 14;          // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (p.K + kTcBK - 1) / kTcBK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTcEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int i = 0;
+            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++i) {
+                const int ab = i & 1;
+                mbar_wait(&a_empty[ab], (((uint32_t)i >> 1) & 1) ^ 1);
+                mbar_expect_tx(&a_full[ab], (uint32_t)(num_kb * kTcABytes));
+                for (int kb = 0; kb < num_kb; ++kb)
+                    tma_load_2d(s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes, &tmA, &a_full[ab], kb * kTcBK, mt * kTcBM);
+                for (int nt = 0; nt < p.n_tiles; ++nt)
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&b_empty[stage], phase ^ 1);
+                        mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
+                        tma_load_2d(s_b + (size_t)stage * b_bytes, &tmB, &b_full[stage], kb * kTcBK, nt * p.BN);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc(kTcBM, p.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int i = 0, t = 0;
+            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++i) {
+                const int ab = i & 1;
+                mbar_wait(&a_full[ab], ((uint32_t)i >> 1) & 1);
+                for (int nt = 0; nt < p.n_tiles; ++nt, ++t) {
+                    const int acc = t & 1;
+                    mbar_wait(&acc_empty[acc], (((uint32_t)t >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&b_full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t adesc = tc_smem_desc(smem_u32(s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes));
+                        const uint64_t bdesc = tc_smem_desc(smem_u32(s_b + (size_t)stage * b_bytes));
+#pragma unroll
+                        for (int k = 0; k < kTcBK / 16; ++k)     // advance 16 K-elements = 32 B inside the swizzle atom (>>4 = 2)
+                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        tc_commit(&b_empty[stage]);                  // W stage reusable once these MMAs have read it
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&acc_full[acc]);                       // accumulator complete
+                }
+                tc_commit(&a_empty[ab]);                             // every MMA that reads this A tile has been issued
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..17): TMEM lane quadrant = warp % 4, column groups striped by 4 =================
+        const int q = warp & 3;
+        const int cgp = (warp - 2) >> 2;
+        const int ngroups = p.BN >> 4;
+        int t = 0;
+        for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+            const long long row = (long long)mt * kTcBM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            __half* c_row = p.C + row * p.N;
+            for (int nt = 0; nt < p.n_tiles; ++nt, ++t) {
+                const int acc = t & 1;
+                mbar_wait(&acc_full[acc], ((uint32_t)t >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+                const int n0 = nt * p.BN;
+                uint32_t v[4][16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int g = cgp + 4 * j;
+                    if (g < ngroups) tc_ld16(t_row + (uint32_t)(g * 16), v[j]);
+                }
+                tc_wait_ld();
+                // TMEM reads are complete: hand the accumulator back before doing the math / stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int g = cgp + 4 * j;
+                    if (g < ngroups) {
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + g * 16);
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float4 b = __ldg(bp + h);
+                            float x0 = __uint_as_float(v[j][4 * h]) + b.x, x1 = __uint_as_float(v[j][4 * h + 1]) + b.y;
+                            float x2 = __uint_as_float(v[j][4 * h + 2]) + b.z, x3 = __uint_as_float(v[j][4 * h + 3]) + b.w;
+                            if (p.act) { x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3); }
+                            pk[2 * h] = pack_half2(x0, x1);
+                            pk[2 * h + 1] = pack_half2(x2, x3);
+                        }
+                        if (row_ok) st_global_v8(c_row + n0 + g * 16, pk);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace mds

@@ -2,8 +2,11 @@
 // See include/mds_b200.h for the contract of every exported function.
 #include "../../include/mds_b200.h"
 
+#include <cudaTypedefs.h>
+
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -13,6 +16,7 @@
 #include "conv3x3.cuh"
 #include "dwconv.cuh"
 #include "gemm1x1.cuh"
+#include "gemm_tc.cuh"
 #include "se_head.cuh"
 #include "stem.cuh"
 
@@ -184,10 +188,77 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
     return MDS_OK;
 }
 
+// ---- tcgen05 path: TMA tensor maps are encoded on the host through the driver entry point (no libcuda link) ----
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// fp16 row-major [rows][K] matrix, box = 64 (K) x box_rows, 128-byte swizzle, out-of-bounds elements read as zero
+static int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int K, int box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d box_rows=%d", (int)r, rows, K, box_rows);
+    return MDS_OK;
+}
+
+static int tc_pick_bn(int N) {
+    if (N <= 256) return N;
+    const int cand[] = {256, 224, 192, 160, 128, 112, 96, 64};
+    for (int c : cand) if (N % c == 0) return c;
+    return 0;
+}
+
+static int launch_gemm_tc(const __half* A, const __half* W, const float* bias, __half* C, long long M, int N, int K, int act,
+                          cudaStream_t st) {
+    const int BN = tc_pick_bn(N);
+    if (BN == 0 || BN % 16 || K > kTcMaxKB * kTcBK) return fail(MDS_ERR_INVALID, "gemm_tc: unsupported N=%d K=%d", N, K);
+    CUtensorMap tmA, tmB;
+    TRY(make_tmap_2d(&tmA, A, M, K, kTcBM));
+    TRY(make_tmap_2d(&tmB, W, N, K, BN));
+    TcGemmParams p;
+    p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.BN = BN; p.act = act;
+    p.m_tiles = (int)((M + kTcBM - 1) / kTcBM);
+    p.n_tiles = N / BN;
+    p.stages = tc_stages(BN);
+    int cols = 32;
+    while (cols < 2 * BN) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t smem = tc_smem_bytes(BN);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    int grid = num_sms();
+    if (p.m_tiles < grid) grid = p.m_tiles;
+    ProfScope ps(MDS_KIND_GEMM1X1, st);
+    gemm_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+    LAUNCH_CHECK("gemm_tc");
+    return MDS_OK;
+}
+
 static int launch_gemm(const __half* A, const __half* W, const float* bias, const __half* res, const __half* gate,
                        __half* C, long long rows_per_img, int n_img, int N, int K, int act, cudaStream_t st) {
     if (K % 16 || N % 16 || K > 1152) return fail(MDS_ERR_INVALID, "gemm1x1: N, K must be multiples of 16, K <= 1152 (N=%d K=%d)", N, K);
     if (rows_per_img <= 0 || n_img <= 0) return MDS_OK;
+    static const bool use_tc = [] { const char* e = getenv("MDS_GEMM_TC"); return !(e && e[0] == '0'); }();
+    if (use_tc && gate == nullptr && res == nullptr && K <= kTcMaxKB * kTcBK && rows_per_img * n_img < (1LL << 31) && tc_pick_bn(N) > 0)
+        return launch_gemm_tc(A, W, bias, C, rows_per_img * n_img, N, K, act, st);
     // The M-tile index lives in gridDim.y (<= 65535): split very large ungated problems into row slabs.
     const long long max_rows = 65535LL * kGemmBM;
     if (gate == nullptr && rows_per_img * n_img > max_rows) {
