@@ -39,7 +39,7 @@ SIGNATURES = {
     "mds_nhwc16_to_nchw32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mds_k_stem": (_i, [_FP, _i, _vp, _vp, _vp, _vp]),
     "mds_k_conv3x3": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "mds_k_gemm1x1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mds_k_gemm1x1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mds_k_dwconv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mds_k_se_fc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mds_k_gem": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp]),

@@ -10,6 +10,8 @@
 //     tcgen05.commit to release smem and to publish finished accumulators;
 //   * warps 2-17      : epilogue — tcgen05.ld 16 accumulator columns per request, bias + SiLU in fp32, one rounding
 //     to fp16, one 32-byte (full sector) st.global.v8 per request; no smem staging;
+//   * the bias is added by the tensor core: one extra K=16 MMA per tile multiplies a constant "ones" A tile with a
+//     [N][64] fp16 matrix holding bias as a hi/lo pair (exact to ~2^-22), so the epilogue has no loads at all;
 //   * two accumulators (2*BN TMEM columns): the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -19,7 +21,6 @@
 namespace mds {
 
 struct TcGemmParams {
-    const float* bias;    // [N]
     __half* C;            // [M][N]
     long long M;
     int N, K, BN;
@@ -36,7 +37,7 @@ constexpr int kTcABytes = kTcBM * kTcBK * 2;          // 16 KB per K block
 
 __host__ __device__ inline int tc_stages(int BN) { return BN > 192 ? 3 : 4; }
 __host__ __device__ inline size_t tc_smem_bytes(int BN) {
-    return 1024 /*align slack*/ + (size_t)2 * kTcMaxKB * kTcABytes + (size_t)tc_stages(BN) * BN * 128 + 256 /*barriers*/;
+    return 1024 /*align slack*/ + (size_t)(2 * kTcMaxKB + 1) * kTcABytes + (size_t)tc_stages(BN) * BN * 128 + 256 /*barriers*/;
 }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------
@@ -114,12 +115,14 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) 
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcGemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBias, TcGemmParams p) {
     extern __shared__ unsigned char tc_smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* s_a = smem;                                           // [2][kTcMaxKB][16 KB]
-    unsigned char* s_b = smem + (size_t)2 * kTcMaxKB * kTcABytes;        // [stages][BN * 128 B]
+    unsigned char* s_ones = smem + (size_t)2 * kTcMaxKB * kTcABytes;     // 128x64 tile: columns 0,1 = 1.0, rest 0
+    unsigned char* s_b = s_ones + kTcABytes;                             // [stages][BN * 128 B]
     const int b_bytes = p.BN * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + (size_t)p.stages * b_bytes);
     uint64_t* b_full = bars;                  // [4]
@@ -137,12 +140,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTcEpiWarps);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTcEpiWarps / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBias) : "memory");
     }
+    // ones tile in the 128-byte-swizzled K-major layout: element (r, 0..7) lives in 16-byte chunk (0 ^ (r & 7)) of row r
+    for (int i = threadIdx.x; i < kTcABytes / 16; i += kTcThreads) {
+        const int r = i >> 3, ch = i & 7;
+        reinterpret_cast<uint4*>(s_ones)[i] = (ch == (r & 7)) ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -157,18 +167,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int i = 0;
-            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++i) {
+            auto load_a = [&](int i, int mt) {      // A row tile i of this CTA -> buffer i & 1
                 const int ab = i & 1;
                 mbar_wait(&a_empty[ab], (((uint32_t)i >> 1) & 1) ^ 1);
                 mbar_expect_tx(&a_full[ab], (uint32_t)(num_kb * kTcABytes));
                 for (int kb = 0; kb < num_kb; ++kb)
                     tma_load_2d(s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes, &tmA, &a_full[ab], kb * kTcBK, mt * kTcBM);
+            };
+            int i = 0;
+            if ((int)blockIdx.x < p.m_tiles) load_a(0, blockIdx.x);
+            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++i) {
+                // the next row tile's A is requested a whole tile ahead, so its HBM latency hides behind this tile
+                if (mt + (int)gridDim.x < p.m_tiles) load_a(i + 1, mt + gridDim.x);
                 for (int nt = 0; nt < p.n_tiles; ++nt)
-                    for (int kb = 0; kb < num_kb; ++kb) {
+                    for (int kb = 0; kb <= num_kb; ++kb) {              // block num_kb = the bias block
                         mbar_wait(&b_empty[stage], phase ^ 1);
                         mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
-                        tma_load_2d(s_b + (size_t)stage * b_bytes, &tmB, &b_full[stage], kb * kTcBK, nt * p.BN);
+                        if (kb < num_kb) tma_load_2d(s_b + (size_t)stage * b_bytes, &tmB, &b_full[stage], kb * kTcBK, nt * p.BN);
+                        else tma_load_2d(s_b + (size_t)stage * b_bytes, &tmBias, &b_full[stage], 0, nt * p.BN);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
             }
@@ -188,13 +204,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&acc_empty[acc], (((uint32_t)t >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                    for (int kb = 0; kb < num_kb; ++kb) {
+                    for (int kb = 0; kb <= num_kb; ++kb) {
                         mbar_wait(&b_full[stage], phase);
                         tc_fence_after();
-                        const uint64_t adesc = tc_smem_desc(smem_u32(s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes));
+                        const bool bias_blk = kb == num_kb;
+                        const uint64_t adesc = tc_smem_desc(smem_u32(bias_blk ? s_ones : s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes));
                         const uint64_t bdesc = tc_smem_desc(smem_u32(s_b + (size_t)stage * b_bytes));
-#pragma unroll
-                        for (int k = 0; k < kTcBK / 16; ++k)     // advance 16 K-elements = 32 B inside the swizzle atom (>>4 = 2)
+                        const int nk = bias_blk ? 1 : kTcBK / 16;       // the bias block only has K = 16 worth of data
+                        for (int k = 0; k < nk; ++k)     // advance 16 K-elements = 32 B inside the swizzle atom (>>4 = 2)
                             tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                         tc_commit(&b_empty[stage]);                  // W stage reusable once these MMAs have read it
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -205,9 +222,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ================= epilogue (warps 2..17): TMEM lane quadrant = warp % 4, column groups striped by 4 =================
+        // ================= epilogue (warps 2..17) =================
+        // Two groups of 8 warps; group e drains accumulator e (tiles t with t % 2 == e), so the TMEM reads and stores of
+        // one tile overlap the bias/SiLU math of the other.  TMEM lane quadrant = warp % 4; the two warps of a group
+        // that share a quadrant take alternate 16-column groups.
         const int q = warp & 3;
-        const int cgp = (warp - 2) >> 2;
+        const int e = ((warp - 2) >> 2) & 1;
+        const int half = (warp - 2) >> 3;
         const int ngroups = p.BN >> 4;
         int t = 0;
         for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
@@ -215,38 +236,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool row_ok = row < p.M;
             __half* c_row = p.C + row * p.N;
             for (int nt = 0; nt < p.n_tiles; ++nt, ++t) {
-                const int acc = t & 1;
-                mbar_wait(&acc_full[acc], ((uint32_t)t >> 1) & 1);
+                if ((t & 1) != e) continue;
+                mbar_wait(&acc_full[e], ((uint32_t)t >> 1) & 1);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e * p.BN);
                 const int n0 = nt * p.BN;
-                uint32_t v[4][16];
+                for (int g0 = half; g0 < ngroups; g0 += 8) {       // up to 4 column groups (64 accumulator columns) per pass
+                    uint32_t v[4][16];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int g = cgp + 4 * j;
-                    if (g < ngroups) tc_ld16(t_row + (uint32_t)(g * 16), v[j]);
-                }
-                tc_wait_ld();
-                // TMEM reads are complete: hand the accumulator back before doing the math / stores
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    for (int j = 0; j < 4; ++j) {
+                        const int g = g0 + 2 * j;
+                        if (g < ngroups) tc_ld16(t_row + (uint32_t)(g * 16), v[j]);
+                    }
+                    tc_wait_ld();
+                    if (g0 + 8 >= ngroups) {
+                        // last TMEM read of this tile: hand the accumulator back before doing the math / stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[e]);
+                    }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int g = cgp + 4 * j;
-                    if (g < ngroups) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + g * 16);
-                        uint32_t pk[8];
+                    for (int j = 0; j < 4; ++j) {
+                        const int g = g0 + 2 * j;
+                        if (g < ngroups) {
+                            uint32_t pk[8];
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const float4 b = __ldg(bp + h);
-                            float x0 = __uint_as_float(v[j][4 * h]) + b.x, x1 = __uint_as_float(v[j][4 * h + 1]) + b.y;
-                            float x2 = __uint_as_float(v[j][4 * h + 2]) + b.z, x3 = __uint_as_float(v[j][4 * h + 3]) + b.w;
-                            if (p.act) { x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3); }
-                            pk[2 * h] = pack_half2(x0, x1);
-                            pk[2 * h + 1] = pack_half2(x2, x3);
+                            for (int h = 0; h < 4; ++h) {
+                                float x0 = __uint_as_float(v[j][4 * h]), x1 = __uint_as_float(v[j][4 * h + 1]);
+                                float x2 = __uint_as_float(v[j][4 * h + 2]), x3 = __uint_as_float(v[j][4 * h + 3]);
+                                if (p.act) { x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3); }
+                                pk[2 * h] = pack_half2(x0, x1);
+                                pk[2 * h + 1] = pack_half2(x2, x3);
+                            }
+                            if (row_ok) st_global_v8(c_row + n0 + g * 16, pk);
                         }
-                        if (row_ok) st_global_v8(c_row + n0 + g * 16, pk);
                     }
                 }
             }

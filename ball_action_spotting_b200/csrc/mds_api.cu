@@ -223,15 +223,16 @@ static int tc_pick_bn(int N) {
     return 0;
 }
 
-static int launch_gemm_tc(const __half* A, const __half* W, const float* bias, __half* C, long long M, int N, int K, int act,
+static int launch_gemm_tc(const __half* A, const __half* W, const __half* bias_mat, __half* C, long long M, int N, int K, int act,
                           cudaStream_t st) {
     const int BN = tc_pick_bn(N);
-    if (BN == 0 || BN % 16 || K > kTcMaxKB * kTcBK) return fail(MDS_ERR_INVALID, "gemm_tc: unsupported N=%d K=%d", N, K);
-    CUtensorMap tmA, tmB;
+    if (BN < 32 || BN % 16 || K > kTcMaxKB * kTcBK) return fail(MDS_ERR_INVALID, "gemm_tc: unsupported N=%d K=%d", N, K);
+    CUtensorMap tmA, tmB, tmBias;
     TRY(make_tmap_2d(&tmA, A, M, K, kTcBM));
     TRY(make_tmap_2d(&tmB, W, N, K, BN));
+    TRY(make_tmap_2d(&tmBias, bias_mat, N, kTcBK, BN));
     TcGemmParams p;
-    p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.BN = BN; p.act = act;
+    p.C = C; p.M = M; p.N = N; p.K = K; p.BN = BN; p.act = act;
     p.m_tiles = (int)((M + kTcBM - 1) / kTcBM);
     p.n_tiles = N / BN;
     p.stages = tc_stages(BN);
@@ -247,18 +248,20 @@ static int launch_gemm_tc(const __half* A, const __half* W, const float* bias, _
     int grid = num_sms();
     if (p.m_tiles < grid) grid = p.m_tiles;
     ProfScope ps(MDS_KIND_GEMM1X1, st);
-    gemm_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+    gemm_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, tmBias, p);
     LAUNCH_CHECK("gemm_tc");
     return MDS_OK;
 }
 
+// bias_mat: [N][64] fp16, column 0 = fp16(bias), column 1 = fp16(bias - column 0), rest 0 (packer.py); enables the tcgen05 path
 static int launch_gemm(const __half* A, const __half* W, const float* bias, const __half* res, const __half* gate,
-                       __half* C, long long rows_per_img, int n_img, int N, int K, int act, cudaStream_t st) {
+                       __half* C, long long rows_per_img, int n_img, int N, int K, int act, cudaStream_t st,
+                       const __half* bias_mat = nullptr) {
     if (K % 16 || N % 16 || K > 1152) return fail(MDS_ERR_INVALID, "gemm1x1: N, K must be multiples of 16, K <= 1152 (N=%d K=%d)", N, K);
     if (rows_per_img <= 0 || n_img <= 0) return MDS_OK;
     static const bool use_tc = [] { const char* e = getenv("MDS_GEMM_TC"); return !(e && e[0] == '0'); }();
-    if (use_tc && gate == nullptr && res == nullptr && K <= kTcMaxKB * kTcBK && rows_per_img * n_img < (1LL << 31) && tc_pick_bn(N) > 0)
-        return launch_gemm_tc(A, W, bias, C, rows_per_img * n_img, N, K, act, st);
+    if (use_tc && bias_mat != nullptr && gate == nullptr && res == nullptr && K <= kTcMaxKB * kTcBK && rows_per_img * n_img < (1LL << 31) && tc_pick_bn(N) >= 32)
+        return launch_gemm_tc(A, W, bias_mat, C, rows_per_img * n_img, N, K, act, st);
     // The M-tile index lives in gridDim.y (<= 65535): split very large ungated problems into row slabs.
     const long long max_rows = 65535LL * kGemmBM;
     if (gate == nullptr && rows_per_img * n_img > max_rows) {
@@ -376,12 +379,12 @@ struct Block2d {
     char kind;   // 'c' ConvBnAct, 'e' EdgeResidual, 'i' InvertedResidual
     int cin, mid, cout, stride, rd;
     bool skip;
-    const __half *w1 = nullptr, *w2 = nullptr, *wpw = nullptr, *wpwl = nullptr;
+    const __half *w1 = nullptr, *w2 = nullptr, *wpw = nullptr, *wpwl = nullptr, *bmpw = nullptr;
     const float *b1 = nullptr, *b2 = nullptr, *bpw = nullptr, *bpwl = nullptr;
     const float *wdw = nullptr, *bdw = nullptr, *se_w1 = nullptr, *se_b1 = nullptr, *se_w2t = nullptr, *se_b2 = nullptr;
 };
 struct Block3d {
-    const __half *wpw, *wpwl;
+    const __half *wpw, *wpwl, *bmpw;
     const float *bpw, *bpwl, *wdw, *bdw, *se_w1, *se_b1, *se_w2t, *se_b2;
 };
 
@@ -391,7 +394,7 @@ struct MdsHandle {
     bool committed = false;
     const float *stem_w = nullptr, *stem_b = nullptr;
     std::vector<Block2d> blocks;
-    const __half *proj2d_w = nullptr, *proj3d_w = nullptr;
+    const __half *proj2d_w = nullptr, *proj3d_w = nullptr, *proj2d_bm = nullptr, *proj3d_bm = nullptr;
     const float *proj2d_b = nullptr, *proj3d_b = nullptr;
     std::vector<Block3d> blocks3d;
     float gem_p = 3.0f;
@@ -497,6 +500,7 @@ extern "C" int mds_weights_commit(MdsHandle* h) {
             } else {
                 TRY(get_tensor(h, p + "pw.w", (size_t)b.mid * b.cin, &b.wpw));
                 TRY(get_tensor(h, p + "pw.b", b.mid, &b.bpw));
+                TRY(get_tensor(h, p + "pw.bm", (size_t)b.mid * 64, &b.bmpw));
                 TRY(get_tensor(h, p + "dw.w", (size_t)9 * b.mid, &b.wdw));
                 TRY(get_tensor(h, p + "dw.b", b.mid, &b.bdw));
                 TRY(get_tensor(h, p + "se.w1", (size_t)b.rd * b.mid, &b.se_w1));
@@ -513,6 +517,7 @@ extern "C" int mds_weights_commit(MdsHandle* h) {
     const int c3 = h->cfg.num_3d_features, mid = h->mid3d(), rd = h->rd3d(), pj = h->cfg.num_3d_stack_proj;
     TRY(get_tensor(h, "proj2d.w", (size_t)c3 * 192, &h->proj2d_w));
     TRY(get_tensor(h, "proj2d.b", c3, &h->proj2d_b));
+    TRY(get_tensor(h, "proj2d.bm", (size_t)c3 * 64, &h->proj2d_bm));
     for (int i = 0; i < h->cfg.num_3d_blocks; ++i) {
         Block3d b;
         char pre[32];
@@ -520,6 +525,7 @@ extern "C" int mds_weights_commit(MdsHandle* h) {
         const std::string p(pre);
         TRY(get_tensor(h, p + "pw.w", (size_t)mid * c3, &b.wpw));
         TRY(get_tensor(h, p + "pw.b", mid, &b.bpw));
+        TRY(get_tensor(h, p + "pw.bm", (size_t)mid * 64, &b.bmpw));
         TRY(get_tensor(h, p + "dw.w", (size_t)27 * mid, &b.wdw));
         TRY(get_tensor(h, p + "dw.b", mid, &b.bdw));
         TRY(get_tensor(h, p + "se.w1", (size_t)rd * mid, &b.se_w1));
@@ -532,6 +538,7 @@ extern "C" int mds_weights_commit(MdsHandle* h) {
     }
     TRY(get_tensor(h, "proj3d.w", (size_t)pj * c3, &h->proj3d_w));
     TRY(get_tensor(h, "proj3d.b", pj, &h->proj3d_b));
+    TRY(get_tensor(h, "proj3d.bm", (size_t)pj * 64, &h->proj3d_bm));
     const float* gp = nullptr;
     TRY(get_tensor(h, "gem.p", 1, &gp));
     CUDA_TRY(cudaMemcpy(&h->gem_p, gp, sizeof(float), cudaMemcpyDeviceToHost));
@@ -653,7 +660,7 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
             } else if (b.kind == 'e') {
                 TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, b.w2, b.b2, cs, hh, ww, b.cin, b.mid, b.stride, b.cout, b.skip, st));
             } else {
-                TRY(launch_gemm(X[cur], b.wpw, b.bpw, nullptr, nullptr, M1, (long long)hh * ww, cs, b.mid, b.cin, 1, st));
+                TRY(launch_gemm(X[cur], b.wpw, b.bpw, nullptr, nullptr, M1, (long long)hh * ww, cs, b.mid, b.cin, 1, st, b.bmpw));
                 TRY(launch_dw(M1, M2, b.wdw, b.bdw, sums, cs, 1, hh, ww, b.mid, 1, b.stride, st));
                 TRY(launch_se(sums, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, cs, b.mid, b.rd, 1.0f / (float)(ho * wo), st));
                 TRY(launch_gemm(M2, b.wpwl, b.bpwl, b.skip ? X[cur] : nullptr, gate, X[cur ^ 1], (long long)ho * wo, cs, b.cout, b.mid, 0, st));
@@ -662,7 +669,7 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
         }
         ++g_prof_tag;
         TRY(launch_gemm(X[cur], h->proj2d_w, h->proj2d_b, nullptr, nullptr, feats_out + (size_t)i0 * P * 192,
-                        (long long)P, cs, h->cfg.num_3d_features, 192, 1, st));
+                        (long long)P, cs, h->cfg.num_3d_features, 192, 1, st, h->proj2d_bm));
     }
     return MDS_OK;
 }
@@ -689,7 +696,7 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
     g_prof_tag = 100;
     for (const Block3d& blk : h->blocks3d) {
         ++g_prof_tag;
-        TRY(launch_gemm(x, blk.wpw, blk.bpw, nullptr, nullptr, M1, (long long)T * P, b, mid, c3, 1, st));
+        TRY(launch_gemm(x, blk.wpw, blk.bpw, nullptr, nullptr, M1, (long long)T * P, b, mid, c3, 1, st, blk.bmpw));
         TRY(launch_dw(M1, M2, blk.wdw, blk.bdw, sums, b, T, fh, fw, mid, 3, 1, st));
         TRY(launch_se(sums, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, b, mid, rd, 1.0f / (float)((size_t)T * P), st));
         TRY(launch_gemm(M2, blk.wpwl, blk.bpwl, x, gate, Y[nxt], (long long)T * P, b, c3, mid, 0, st));
@@ -697,7 +704,7 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
         nxt ^= 1;
     }
     g_prof_tag = 150;
-    TRY(launch_gemm(x, h->proj3d_w, h->proj3d_b, nullptr, nullptr, out, (long long)T * P, b, h->cfg.num_3d_stack_proj, c3, 1, st));
+    TRY(launch_gemm(x, h->proj3d_w, h->proj3d_b, nullptr, nullptr, out, (long long)T * P, b, h->cfg.num_3d_stack_proj, c3, 1, st, h->proj3d_bm));
     return MDS_OK;
 }
 
@@ -793,11 +800,12 @@ extern "C" int mds_k_conv3x3(const void* in, void* out, const void* w1, const fl
                         b1, reinterpret_cast<const __half*>(w2), b2, n, H, W, cin, cmid, stride, cproj, res,
                         reinterpret_cast<cudaStream_t>(stream));
 }
-extern "C" int mds_k_gemm1x1(const void* A, const void* W, const float* bias, const void* res, const void* gate, void* C,
-                             int rows_per_img, int n_img, int N, int K, int act, void* stream) {
+extern "C" int mds_k_gemm1x1(const void* A, const void* W, const float* bias, const void* bias_mat, const void* res,
+                             const void* gate, void* C, int rows_per_img, int n_img, int N, int K, int act, void* stream) {
     return launch_gemm(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(W), bias,
                        reinterpret_cast<const __half*>(res), reinterpret_cast<const __half*>(gate),
-                       reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream));
+                       reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream),
+                       reinterpret_cast<const __half*>(bias_mat));
 }
 extern "C" int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* sums, int n, int T, int H,
                             int W, int C, int kt, int stride, void* stream) {

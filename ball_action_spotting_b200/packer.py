@@ -34,6 +34,17 @@ def _f(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.float32).contiguous()
 
 
+def bias_matrix(b: torch.Tensor) -> torch.Tensor:
+    """[N][64] fp16 operand of the tcgen05 GEMM's bias MMA: col 0 = fp16(b), col 1 = fp16(b - col 0), rest 0.
+    Multiplied by a ones tile on the tensor core, hi + lo reproduces the fp32 bias to ~2^-22."""
+    b = b.detach().double().cpu()
+    hi = b.to(torch.float16)
+    lo = (b - hi.double()).to(torch.float16)
+    m = torch.zeros((b.numel(), 64), dtype=torch.float16)
+    m[:, 0], m[:, 1] = hi, lo
+    return m.contiguous()
+
+
 def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str, torch.Tensor]:
     out: Dict[str, torch.Tensor] = {}
     e = "conv2d_encoder."
@@ -46,10 +57,12 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str
         out[name + ".w"] = _h(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))   # [co][(r*3+s)*ci + c]
         out[name + ".b"] = _f(b)
 
-    def pw(name, wkey, bn, eps):
+    def pw(name, wkey, bn, eps, bias_mat=False):
         w, b = _fold(sd, wkey, bn, eps)
         out[name + ".w"] = _h(w.reshape(w.shape[0], w.shape[1]))            # [co][ci]
         out[name + ".b"] = _f(b)
+        if bias_mat:
+            out[name + ".bm"] = bias_matrix(b)
 
     def dw(name, wkey, bn, eps):
         w, b = _fold(sd, wkey, bn, eps)                                    # [C][1][(kt)][3][3]
@@ -72,19 +85,19 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str
                 conv3(n + ".c3", p + "conv_exp.weight", p + "bn1")
                 pw(n + ".pwl", p + "conv_pwl.weight", p + "bn2", ENC_EPS)
             else:
-                pw(n + ".pw", p + "conv_pw.weight", p + "bn1", ENC_EPS)
+                pw(n + ".pw", p + "conv_pw.weight", p + "bn1", ENC_EPS, bias_mat=True)
                 dw(n + ".dw", p + "conv_dw.weight", p + "bn2", ENC_EPS)
                 se(n + ".se", p + "se")
                 pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3", ENC_EPS)
 
-    pw("proj2d", "conv2d_projection.0.weight", "conv2d_projection.1", REF_EPS)
+    pw("proj2d", "conv2d_projection.0.weight", "conv2d_projection.1", REF_EPS, bias_mat=True)
     for i in range(num_3d_blocks):
         p, n = f"conv3d_encoder.{i}.", f"c3d.{i}"
-        pw(n + ".pw", p + "conv_pw.weight", p + "bn1.bn3d", REF_EPS)
+        pw(n + ".pw", p + "conv_pw.weight", p + "bn1.bn3d", REF_EPS, bias_mat=True)
         dw(n + ".dw", p + "conv_dw.weight", p + "bn2.bn3d", REF_EPS)
         se(n + ".se", p + "se")
         pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3.bn3d", REF_EPS)
-    pw("proj3d", "conv3d_projection.0.weight", "conv3d_projection.1", REF_EPS)
+    pw("proj3d", "conv3d_projection.0.weight", "conv3d_projection.1", REF_EPS, bias_mat=True)
     out["gem.p"] = _f(sd["global_pool.p"].detach().cpu().reshape(1))
     out["cls.w"] = _f(sd["classifier.weight"].detach().cpu())
     out["cls.b"] = _f(sd["classifier.bias"].detach().cpu())

@@ -96,8 +96,10 @@ int mds_nhwc16_to_nchw32(const void* src, float* dst, int n, int C, int P, void*
 int mds_k_stem(const MdsFrames* frames, int n_images, const float* w, const float* bias, void* out, void* stream);
 int mds_k_conv3x3(const void* in, void* out, const void* w1, const float* b1, const void* w2, const float* b2,
                   int n, int H, int W, int cin, int cmid, int stride, int cproj, int res, void* stream);
-int mds_k_gemm1x1(const void* A, const void* W, const float* bias, const void* res, const void* gate, void* C,
-                  int rows_per_img, int n_img, int N, int K, int act, void* stream);
+/* bias_mat (optional): [N][64] fp16, col 0 = fp16(bias), col 1 = fp16(bias - col 0); selects the tcgen05 kernel for
+ * ungated GEMMs with K <= 192 (the bias is then added by the tensor core). */
+int mds_k_gemm1x1(const void* A, const void* W, const float* bias, const void* bias_mat, const void* res, const void* gate,
+                  void* C, int rows_per_img, int n_img, int N, int K, int act, void* stream);
 int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* sums,
                  int n, int T, int H, int W, int C, int kt, int stride, void* stream);
 int mds_k_se_fc(float* sums, const float* w1, const float* b1, const float* w2t, const float* b2, void* gate,

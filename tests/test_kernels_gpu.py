@@ -127,13 +127,16 @@ def test_gemm1x1(lib, N, K, gated, res, act):
     if res:
         r = h16(torch.randn(M, N, generator=gen(5)))
         y = y + r.float()
+    from ball_action_spotting_b200.packer import bias_matrix
     d = lambda t: None if t is None else t.contiguous().to(DEV)
-    dA, dW, db, dr, dg = d(A), d(Wt), d(bias), d(r), d(g)
-    out = torch.zeros((M, N), dtype=torch.float16, device=DEV)
+    dA, dW, db, dr, dg, dbm = d(A), d(Wt), d(bias), d(r), d(g), d(bias_matrix(bias))
     p = lambda t: None if t is None else t.data_ptr()
-    ok(lib.mds_k_gemm1x1(p(dA), p(dW), p(db), p(dr), p(dg), out.data_ptr(), rows, n_img, N, K, act, None), lib)
-    torch.cuda.synchronize()
-    assert rel(out, y) <= TOL
+    # with bias_mat: ungated K <= 192 cases run on the tcgen05 kernel; without: the mma.sync kernel
+    for bm in (dbm, None):
+        out = torch.zeros((M, N), dtype=torch.float16, device=DEV)
+        ok(lib.mds_k_gemm1x1(p(dA), p(dW), p(db), p(bm), p(dr), p(dg), out.data_ptr(), rows, n_img, N, K, act, None), lib)
+        torch.cuda.synchronize()
+        assert rel(out, y) <= TOL
 
 
 @pytest.mark.parametrize("C_,stride", [(192, 2), (384, 1), (576, 1), (672, 1), (672, 2), (1152, 1)])
@@ -229,7 +232,7 @@ def test_layout_converters_round_trip(lib):
 
 
 def test_errors_are_reported_not_swallowed(lib):
-    rc = lib.mds_k_gemm1x1(None, None, None, None, None, None, 10, 1, 100, 30, 0, None)
+    rc = lib.mds_k_gemm1x1(None, None, None, None, None, None, None, 10, 1, 100, 30, 0, None)
     assert rc != 0 and b"multiples of 16" in lib.mds_last_error()
     rc = lib.mds_k_conv3x3(None, None, None, None, None, None, 1, 8, 8, 7, 7, 1, 0, 0, None)
     assert rc != 0 and b"unsupported" in lib.mds_last_error()
