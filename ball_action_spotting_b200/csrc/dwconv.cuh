@@ -33,8 +33,12 @@ struct DwCfg {
     static constexpr int IW = (STRIDE == 1) ? kDwTWX + 2 : 2 * kDwTWX + 1;   // input columns per row tile
     static constexpr int NV = (STRIDE == 1) ? kDwPXW + 2 : 2 * kDwPXW + 1;   // input columns per warp strip
     static constexpr int ROW_HALVES = IW * kDwCS;
-    static constexpr int STAGE_HALVES = KT * ROW_HALVES;
-    static constexpr int NST = (KT == 3) ? 4 : (STRIDE == 2 ? 6 : 8);
+    static constexpr int RPS = (KT == 3) ? 1 : 2;                            // input rows per stage (one barrier per stage)
+    static constexpr int STEP_HALVES = KT * ROW_HALVES;                      // one input row (x KT planes)
+    static constexpr int STAGE_HALVES = RPS * STEP_HALVES;
+    static constexpr int NST = (KT == 3) ? 4 : (STRIDE == 2 ? 3 : 4);
+    static constexpr int CHUNKS = KT * IW * 8;                               // 16-byte requests per input row
+    static constexpr int SLOTS = (CHUNKS + 255) / 256;
     static constexpr size_t SMEM = (size_t)NST * STAGE_HALVES * 2 + 8 * kDwCS * sizeof(float);
 };
 
@@ -67,20 +71,41 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     const size_t plane = (size_t)p.H * p.W * p.C;
     const __half* in_n = p.in + (size_t)n * p.T * plane;
 
-    auto issue = [&](int k) {
-        __half* st = s_ring + (k % Cfg::NST) * Cfg::STAGE_HALVES;
-        const int yi = yi0 + k;
-        const bool yok = (yi >= 0) && (yi < p.H);
-        for (int idx = tid; idx < KT * Cfg::IW * 8; idx += 256) {
-            const int pl = idx / (Cfg::IW * 8);
-            const int rem = idx - pl * (Cfg::IW * 8);
-            const int px = rem >> 3, c16 = rem & 7;
-            const int xi = xi0 + px;
-            const int ti = (KT == 3) ? t + pl - 1 : t;
-            const int cc = c_slab + c16 * 8;
-            const bool ok = yok && (xi >= 0) && (xi < p.W) && (ti >= 0) && (ti < p.T) && (cc < p.C);
-            const __half* src = ok ? in_n + (size_t)ti * plane + ((size_t)yi * p.W + xi) * p.C + cc : p.in;
-            cp_async16(st + pl * Cfg::ROW_HALVES + px * kDwCS + c16 * 8, src, ok ? 16 : 0);
+    // cp.async bookkeeping that does not depend on the row is computed once per thread
+    int s_off[Cfg::SLOTS];            // halves, inside one row step
+    long long g_off[Cfg::SLOTS];      // elements from in_n for row 0
+    bool s_ok[Cfg::SLOTS];
+#pragma unroll
+    for (int sl = 0; sl < Cfg::SLOTS; ++sl) {
+        const int idx = tid + sl * 256;
+        const int pl = idx / (Cfg::IW * 8);
+        const int rem = idx - pl * (Cfg::IW * 8);
+        const int px = rem >> 3, c16 = rem & 7;
+        const int xi = xi0 + px;
+        const int ti = (KT == 3) ? t + pl - 1 : t;
+        const int cc = c_slab + c16 * 8;
+        s_ok[sl] = (idx < Cfg::CHUNKS) && (xi >= 0) && (xi < p.W) && (ti >= 0) && (ti < p.T) && (cc < p.C);
+        s_off[sl] = pl * Cfg::ROW_HALVES + px * kDwCS + c16 * 8;
+        g_off[sl] = (long long)ti * (long long)plane + (long long)xi * p.C + cc;
+        if (idx >= Cfg::CHUNKS) s_off[sl] = -1;
+    }
+    const long long row_pitch = (long long)p.W * p.C;
+
+    // stage j holds input rows [j*RPS, j*RPS + RPS) of this chunk
+    auto issue = [&](int j) {
+        __half* st = s_ring + (j % Cfg::NST) * Cfg::STAGE_HALVES;
+#pragma unroll
+        for (int rr = 0; rr < Cfg::RPS; ++rr) {
+            const int yi = yi0 + j * Cfg::RPS + rr;
+            const bool yok = (yi >= 0) && (yi < p.H);
+            const __half* row = in_n + (long long)yi * row_pitch;
+#pragma unroll
+            for (int sl = 0; sl < Cfg::SLOTS; ++sl) {
+                if (s_off[sl] >= 0) {
+                    const bool ok = yok && s_ok[sl];
+                    cp_async16(st + rr * Cfg::STEP_HALVES + s_off[sl], ok ? row + g_off[sl] : p.in, ok ? 16 : 0);
+                }
+            }
         }
     };
 
@@ -90,9 +115,10 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     for (int i = 0; i < KT * 9; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)i * p.C + c_ld));
     const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + c_ld));
 
+    const int NSTG = (NR + Cfg::RPS - 1) / Cfg::RPS;     // stages to stream (rows past NR are loaded but unused)
 #pragma unroll
-    for (int k = 0; k < Cfg::NST - 1; ++k) {
-        if (k < NR) issue(k);
+    for (int j = 0; j < Cfg::NST - 1; ++j) {
+        if (j < NSTG) issue(j);
         cp_async_commit();
     }
 
@@ -103,74 +129,82 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
 
     const int xw = xo0 + warp * kDwPXW;               // first output column of this warp
     const int px_base = (STRIDE == 1) ? warp * kDwPXW : 2 * warp * kDwPXW;
-    __half* out_base = p.out + ((size_t)n * p.T + t) * (size_t)p.Ho * p.Wo * p.C + c;
+    const long long out_pitch = (long long)p.Wo * p.C;
+    __half* out_base = p.out + ((size_t)n * p.T + t) * (size_t)p.Ho * out_pitch + (long long)xw * p.C + c;
+    bool px_ok[kDwPXW];
+#pragma unroll
+    for (int j = 0; j < kDwPXW; ++j) px_ok[j] = c_ok && (xw + j < p.Wo);
 
     auto emit = [&](int yo, const float2 (&acc)[kDwPXW]) {
-        __half* row = out_base + ((size_t)yo * p.Wo + xw) * p.C;
+        __half* row = out_base + (long long)yo * out_pitch;
 #pragma unroll
         for (int j = 0; j < kDwPXW; ++j) {
-            if (c_ok && xw + j < p.Wo) {
+            if (px_ok[j]) {
                 const float ox = silu_f(acc[j].x + bias.x), oy = silu_f(acc[j].y + bias.y);
                 lsum.x += ox; lsum.y += oy;
-                *reinterpret_cast<uint32_t*>(row + (size_t)j * p.C) = pack_half2(ox, oy);
+                *reinterpret_cast<uint32_t*>(row + j * p.C) = pack_half2(ox, oy);
             }
         }
     };
 
-    for (int k = 0; k < NR; ++k) {
+    for (int js = 0; js < NSTG; ++js) {
         cp_async_wait<Cfg::NST - 2>();
         __syncthreads();
-        if (k + Cfg::NST - 1 < NR) issue(k + Cfg::NST - 1);
+        if (js + Cfg::NST - 1 < NSTG) issue(js + Cfg::NST - 1);
         cp_async_commit();
-
-        const __half* st = s_ring + (k % Cfg::NST) * Cfg::STAGE_HALVES + px_base * kDwCS + 2 * lane;
-        const int yi = yi0 + k;
-
-        if constexpr (STRIDE == 1) {
-            // input row yi feeds out rows yi+1 (kernel row 0), yi (row 1), yi-1 (row 2)
 #pragma unroll
-            for (int j = 0; j < kDwPXW; ++j) a2[j] = make_float2(0.f, 0.f);
+        for (int rr = 0; rr < Cfg::RPS; ++rr) {
+            const int k = js * Cfg::RPS + rr;
+            if (k >= NR) break;
+            const __half* st = s_ring + (js % Cfg::NST) * Cfg::STAGE_HALVES + rr * Cfg::STEP_HALVES + px_base * kDwCS + 2 * lane;
+            const int yi = yi0 + k;
+
+            if constexpr (STRIDE == 1) {
+                // input row yi feeds out rows yi+1 (kernel row 0), yi (row 1), yi-1 (row 2)
 #pragma unroll
-            for (int dt = 0; dt < KT; ++dt) {
+                for (int j = 0; j < kDwPXW; ++j) a2[j] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int dt = 0; dt < KT; ++dt) {
+                    float2 v[Cfg::NV];
+#pragma unroll
+                    for (int i = 0; i < Cfg::NV; ++i)
+                        v[i] = __half22float2(*reinterpret_cast<const __half2*>(st + dt * Cfg::ROW_HALVES + i * kDwCS));
+#pragma unroll
+                    for (int j = 0; j < kDwPXW; ++j)
+#pragma unroll
+                        for (int s = 0; s < 3; ++s) {
+                            a2[j] = ffma2(w[dt * 9 + 0 + s], v[j + s], a2[j]);
+                            a1[j] = ffma2(w[dt * 9 + 3 + s], v[j + s], a1[j]);
+                            a0[j] = ffma2(w[dt * 9 + 6 + s], v[j + s], a0[j]);
+                        }
+                }
+                if (yi - 1 >= yo0) emit(yi - 1, a0);        // yi - 1 < yo1 always holds (yi <= yo1)
+#pragma unroll
+                for (int j = 0; j < kDwPXW; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; }
+            } else {
+                // stride 2: even input row 2yo is kernel row 0 of out yo and kernel row 2 of out yo-1; odd row 2yo+1 is row 1
                 float2 v[Cfg::NV];
 #pragma unroll
-                for (int i = 0; i < Cfg::NV; ++i)
-                    v[i] = __half22float2(*reinterpret_cast<const __half2*>(st + dt * Cfg::ROW_HALVES + i * kDwCS));
+                for (int i = 0; i < Cfg::NV; ++i) v[i] = __half22float2(*reinterpret_cast<const __half2*>(st + i * kDwCS));
+                if ((k & 1) == 0) {       // yi = 2*yo0 + k is even
 #pragma unroll
-                for (int j = 0; j < kDwPXW; ++j)
+                    for (int j = 0; j < kDwPXW; ++j) {
+                        a2[j] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        a2[j] = ffma2(w[dt * 9 + 0 + s], v[j + s], a2[j]);
-                        a1[j] = ffma2(w[dt * 9 + 3 + s], v[j + s], a1[j]);
-                        a0[j] = ffma2(w[dt * 9 + 6 + s], v[j + s], a0[j]);
+                        for (int s = 0; s < 3; ++s) {
+                            a1[j] = ffma2(w[6 + s], v[2 * j + s], a1[j]);     // closes out row (yi/2 - 1)
+                            a2[j] = ffma2(w[0 + s], v[2 * j + s], a2[j]);     // opens out row yi/2
+                        }
                     }
-            }
-            if (yi - 1 >= yo0) emit(yi - 1, a0);        // yi - 1 < yo1 always holds (yi <= yo1)
+                    if (k > 0) emit((yi >> 1) - 1, a1);
 #pragma unroll
-            for (int j = 0; j < kDwPXW; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; }
-        } else {
-            // stride 2: even input row 2yo is kernel row 0 of out yo and kernel row 2 of out yo-1; odd row 2yo+1 is row 1
-            float2 v[Cfg::NV];
+                    for (int j = 0; j < kDwPXW; ++j) a1[j] = a2[j];
+                } else {
 #pragma unroll
-            for (int i = 0; i < Cfg::NV; ++i) v[i] = __half22float2(*reinterpret_cast<const __half2*>(st + i * kDwCS));
-            if ((k & 1) == 0) {       // yi = 2*yo0 + k is even
+                    for (int j = 0; j < kDwPXW; ++j)
 #pragma unroll
-                for (int j = 0; j < kDwPXW; ++j) {
-                    a2[j] = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        a1[j] = ffma2(w[6 + s], v[2 * j + s], a1[j]);     // closes out row (yi/2 - 1)
-                        a2[j] = ffma2(w[0 + s], v[2 * j + s], a2[j]);     // opens out row yi/2
-                    }
+                        for (int s = 0; s < 3; ++s) a1[j] = ffma2(w[3 + s], v[2 * j + s], a1[j]);
                 }
-                if (k > 0) emit((yi >> 1) - 1, a1);
-#pragma unroll
-                for (int j = 0; j < kDwPXW; ++j) a1[j] = a2[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < kDwPXW; ++j)
-#pragma unroll
-                    for (int s = 0; s < 3; ++s) a1[j] = ffma2(w[3 + s], v[2 * j + s], a1[j]);
             }
         }
     }
