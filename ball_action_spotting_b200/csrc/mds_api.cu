@@ -114,15 +114,15 @@ static int num_sms() {
 // --------------------------------------------------------------------------------------------------------------
 // kernel launchers
 // --------------------------------------------------------------------------------------------------------------
-static int launch_stem(const MdsFrames& f, int n, const float* w, const float* bias, __half* out, cudaStream_t st) {
+static int launch_stem(const MdsFrames& f, int n, const __half* wh, const float* bias, __half* out, cudaStream_t st) {
     if (f.H % 2 || f.W % 4 || f.H <= 0 || f.W <= 0) return fail(MDS_ERR_INVALID, "stem: H must be even, W a multiple of 4");
     if (f.img_stride % 4 || f.plane_stride % 4) return fail(MDS_ERR_INVALID, "stem: image / plane strides must be multiples of 4 elements");
     if (n <= 0) return MDS_OK;
     StemParams p;
     p.in = f.data; p.img_stride = f.img_stride; p.plane_stride = f.plane_stride;
     p.stored_h = f.stored_h; p.pad_top = f.pad_top; p.H = f.H; p.W = f.W; p.hflip = f.hflip;
-    p.divisor = f.dtype == 0 ? 255.0f : 1.0f;
-    p.w = w; p.bias = bias; p.out = out;
+    p.scale = f.dtype == 0 ? 1.0f / 255.0f : 1.0f;
+    p.wh = wh; p.bias = bias; p.out = out;
     dim3 grid((f.W / 2 + kStemTW - 1) / kStemTW, (f.H / 2 + kStemTH - 1) / kStemTH, n);
     ProfScope ps(MDS_KIND_STEM, st);
     if (f.dtype == 0) stem_kernel<uint8_t><<<grid, 256, 0, st>>>(p);
@@ -392,7 +392,8 @@ struct MdsHandle {
     MdsConfig cfg;
     std::map<std::string, DevBuf> tensors;
     bool committed = false;
-    const float *stem_w = nullptr, *stem_b = nullptr;
+    const __half* stem_w = nullptr;
+    const float* stem_b = nullptr;
     std::vector<Block2d> blocks;
     const __half *proj2d_w = nullptr, *proj3d_w = nullptr, *proj2d_bm = nullptr, *proj3d_bm = nullptr;
     const float *proj2d_b = nullptr, *proj3d_b = nullptr;
@@ -475,7 +476,7 @@ extern "C" int mds_weights_commit(MdsHandle* h) {
     DeviceGuard g(h->cfg.device);
     h->blocks.clear();
     h->blocks3d.clear();
-    TRY(get_tensor(h, "stem.w", 27 * 32, &h->stem_w));
+    TRY(get_tensor(h, "stem.wh", 2 * 32 * 32, &h->stem_w));
     TRY(get_tensor(h, "stem.b", 32, &h->stem_b));
     int cin = 32;
     for (int si = 0; si < 6; ++si) {
@@ -790,9 +791,10 @@ extern "C" int mds_nhwc16_to_nchw32(const void* src, float* dst, int n, int C, i
     return MDS_OK;
 }
 
-extern "C" int mds_k_stem(const MdsFrames* frames, int n_images, const float* w, const float* bias, void* out, void* stream) {
+extern "C" int mds_k_stem(const MdsFrames* frames, int n_images, const void* wh, const float* bias, void* out, void* stream) {
     if (!frames) return fail(MDS_ERR_INVALID, "null frames");
-    return launch_stem(*frames, n_images, w, bias, reinterpret_cast<__half*>(out), reinterpret_cast<cudaStream_t>(stream));
+    return launch_stem(*frames, n_images, reinterpret_cast<const __half*>(wh), bias, reinterpret_cast<__half*>(out),
+                       reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int mds_k_conv3x3(const void* in, void* out, const void* w1, const float* b1, const void* w2, const float* b2,
                              int n, int H, int W, int cin, int cmid, int stride, int cproj, int res, void* stream) {

@@ -34,6 +34,17 @@ def _f(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.float32).contiguous()
 
 
+def stem_weights(w: torch.Tensor) -> torch.Tensor:
+    """[32][3][3][3] folded stem weights -> fp16 [2][32][32]: (hi, lo) x cout x k with k = (ci*3 + r)*3 + s, k >= 27 zero.
+    hi + lo reproduces the fp32 weight to ~2^-22, so the tensor-core stem is as accurate as an fp32 convolution."""
+    w = w.detach().double().cpu().reshape(32, 27)
+    hi = w.to(torch.float16)
+    lo = (w - hi.double()).to(torch.float16)
+    m = torch.zeros((2, 32, 32), dtype=torch.float16)
+    m[0, :, :27], m[1, :, :27] = hi, lo
+    return m.contiguous()
+
+
 def bias_matrix(b: torch.Tensor) -> torch.Tensor:
     """[N][64] fp16 operand of the tcgen05 GEMM's bias MMA: col 0 = fp16(b), col 1 = fp16(b - col 0), rest 0.
     Multiplied by a ones tile on the tensor core, hi + lo reproduces the fp32 bias to ~2^-22."""
@@ -49,7 +60,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str
     out: Dict[str, torch.Tensor] = {}
     e = "conv2d_encoder."
     w, b = _fold(sd, e + "conv_stem.weight", e + "bn1", ENC_EPS)           # [32][3][3][3]
-    out["stem.w"] = _f(w.permute(1, 2, 3, 0).reshape(27, 32))              # [(ci*3+r)*3+s][co]
+    out["stem.wh"] = stem_weights(w)
     out["stem.b"] = _f(b)
 
     def conv3(name, wkey, bn):

@@ -93,7 +93,8 @@ int mds_nchw32_to_nhwc16(const float* src, void* dst, int n, int C, int P, void*
 int mds_nhwc16_to_nchw32(const void* src, float* dst, int n, int C, int P, void* stream);
 
 /* ---- per-kernel entry points (parity tests, ncu) ---- */
-int mds_k_stem(const MdsFrames* frames, int n_images, const float* w, const float* bias, void* out, void* stream);
+/* wh: fp16 [2][32][32] = (hi, lo) x cout x k, k = (ci*3 + r)*3 + s, columns 27..31 zero (packer.stem_weights) */
+int mds_k_stem(const MdsFrames* frames, int n_images, const void* wh, const float* bias, void* out, void* stream);
 int mds_k_conv3x3(const void* in, void* out, const void* w1, const float* b1, const void* w2, const float* b2,
                   int n, int H, int W, int cin, int cmid, int stride, int cproj, int res, void* stream);
 /* bias_mat (optional): [N][64] fp16, col 0 = fp16(bias), col 1 = fp16(bias - col 0); selects the tcgen05 kernel for

@@ -73,7 +73,8 @@ def test_bn_folding_reproduces_conv_bn(oracle_sd):
     # stem [27][32]
     xs = torch.rand(1, 3, 16, 16, generator=g)
     ref = O._bn(oracle_sd, "conv2d_encoder.bn1", O._conv_same(xs, oracle_sd["conv2d_encoder.conv_stem.weight"], 2), O.ENC_BN_EPS)
-    w = pk["stem.w"].view(3, 3, 3, 32).permute(3, 0, 1, 2)
+    w = (pk["stem.wh"][0].float() + pk["stem.wh"][1].float())[:, :27].reshape(32, 3, 3, 3)
+    assert float(pk["stem.wh"][:, :, 27:].abs().max()) == 0.0
     got = F.conv2d(F.pad(xs, (0, 1, 0, 1)), w, pk["stem.b"], stride=2)
     assert (got - ref).abs().max() / ref.abs().max() < 1e-5
     assert pk["b5.7.se.w2t"].shape == (48, 1152) and pk["cls.w"].shape == (2, 1280)

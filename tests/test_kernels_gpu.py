@@ -56,7 +56,8 @@ def test_stem(lib, dtype, hflip):
         x = x.flip(-1)
     ref = F.silu(F.conv2d(F.pad(x, (0, 1, 0, 1)), w, b, stride=2))
     d_raw = raw.to(DEV)
-    d_w = w.permute(1, 2, 3, 0).reshape(27, 32).contiguous().to(DEV)
+    from ball_action_spotting_b200.packer import stem_weights
+    d_w = stem_weights(w).to(DEV)
     d_b = b.to(DEV)
     out = torch.empty((n, H // 2, W // 2, 32), dtype=torch.float16, device=DEV)
     fr = MdsFrames(d_raw.data_ptr(), dt, 3 * stored_h * W, stored_h * W, stored_h, (H - stored_h) // 2, H, W, hflip)
