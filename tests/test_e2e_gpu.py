@@ -212,3 +212,42 @@ def test_streaming_predictor_full_size_tta(tmp_path, oracle_sd):
         n_pred += 1
         assert record(f"predictor_full_tta.probs[{i}]", (got.cpu() - ref).abs().max().item(), NORTH_STAR_TOL) <= NORTH_STAR_TOL
     assert n_pred == 3
+
+
+@pytest.mark.parametrize("tta", [False, True])
+def test_batched_sweep_equals_streaming_predictor(tmp_path, oracle_sd, tta):
+    """sweep.SlidingSweep (config 4's batched path: triples addressed in place by strides, features gathered per window)
+    must reproduce the per-frame predictor, and both must match the oracle."""
+    from ball_action_spotting_b200 import MultiDimStackerPredictor
+    from ball_action_spotting_b200.sweep import SlidingSweep
+    cfg = O.ModelConfig()
+    params = {"nn_module": ("multidim_stacker", dict(model_name="tf_efficientnetv2_b0.in1k", num_classes=2, num_frames=15,
+                                                     stack_size=3, index_2d_features=4, pretrained=False, num_3d_blocks=4,
+                                                     num_3d_features=192, expansion_3d_ratio=3, se_reduce_3d_ratio=24,
+                                                     num_3d_stack_proj=256, drop_rate=0.2, drop_path_rate=0.2, act_layer="silu")),
+              "frames_processor": ("pad_normalize", {"size": (160, 96), "pad_mode": "constant", "fill_value": 0}),
+              "frame_stack_size": 15, "frame_stack_step": 2, "device": ["cuda:0"]}
+    path = tmp_path / "model-001-0.500000.pth"
+    torch.save({"model_name": "BallActionModel", "params": params, "nn_state_dict": oracle_sd}, path)
+    pred = MultiDimStackerPredictor(path, device=DEV, tta=tta)
+    frames = torch.randint(0, 256, (40, 80, 160), dtype=torch.uint8, generator=torch.Generator().manual_seed(4)).to(DEV)
+    stream = {}
+    for i in range(40):
+        got, p = pred.predict(frames[i], i)
+        if got is not None:
+            stream[p] = got.cpu()
+    assert sorted(stream) == list(range(14, 26))
+    sweep = SlidingSweep(pred.model.nn_module, 15, 2, (160, 96), tta=tta, max_stacks=5)
+    batch = sweep.predict_range(frames, 0, 14, 26).cpu()
+    assert batch.shape == (12, 2)
+    for k, p in enumerate(range(14, 26)):
+        assert record(f"sweep_vs_stream_tta{int(tta)}[{p}]", (batch[k] - stream[p]).abs().max().item(), 1e-3) <= 1e-3
+    # a shard that starts in the middle of the buffer (first_frame offset) and the oracle
+    part = sweep.predict_range(frames[4:], 4, 20, 24).cpu()
+    assert (part - batch[6:10]).abs().max().item() <= 1e-3
+    orc = O.StreamingPredictorOracle(oracle_sd, cfg, 2, (160, 96), tta=tta)
+    for i in range(29):
+        ref, p = orc.predict(frames[i].cpu(), i) if i == 28 else (None, orc.frames.__setitem__(i, O.pad_normalize(frames[i].cpu()[None, None], (160, 96))[0, 0]))
+    assert (batch[0] - ref).abs().max().item() <= tol_for(96, 160)
+    with pytest.raises(RuntimeError, match="need frames"):
+        sweep.predict_range(frames, 0, 10, 12)
