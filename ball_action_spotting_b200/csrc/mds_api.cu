@@ -436,7 +436,7 @@ extern "C" int mds_create(const MdsConfig* cfg, MdsHandle** out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(MDS_ERR_INVALID, "device %d out of range", cfg->device);
     MdsHandle* h = new MdsHandle();
     h->cfg = *cfg;
-    if (h->cfg.chunk_images <= 0) h->cfg.chunk_images = 8;
+    if (h->cfg.chunk_images <= 0) h->cfg.chunk_images = 160;   // one pass for up to 32 stacks; ~41 MB of scratch per image
     *out = h;
     return MDS_OK;
 }

@@ -43,7 +43,7 @@ launch = [(recs[j][0], recs[j][1]) for j in range(n_per_rep)]
 # expected launch list for one chunk of the encoder + 3D
 enc = acc.encoder_launches(H, W, SH)
 s3d = acc.stack3d_launches(H // 32, W // 32, T)
-chunk = eng.cfg.chunk_images or 8
+chunk = eng.cfg.chunk_images or 160
 n_img = a.batch * T
 chunks = -(-n_img // chunk)
 rows = []
