@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
     const int b_kof = (lm & 1) * 8;
     const int g = lane >> 2, tq = lane & 3;
 
+    uint32_t breg[CMID == 16 ? 9 * CIN / 16 : 1][4];      // register-resident weights (CMID == 16 only)
     for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
         __half* cur = s_tile + (it & 1) * Cfg::TILE;
         int nxt = t + gridDim.x;
@@ -112,6 +113,28 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
 
         const uint32_t tile_addr = smem_u32(cur);
         const uint32_t w1_addr = smem_u32(s_w1);
+        if constexpr (CMID == 16) {
+            // 16 output channels: the whole weight matrix (9*CIN x 16) is 9*CIN/4 registers per thread; keeping it in
+            // registers halves the shared-memory traffic of this bandwidth-bound layer (each A fragment feeds only 2 MMAs)
+            if (it == 0) {
+#pragma unroll
+                for (int q = 0; q < 9 * CIN / 16; ++q) ldmatrix_x4(breg[q], w1_addr + 2u * (uint32_t)(b_nof * Cfg::W1P + q * 16 + b_kof));
+            }
+#pragma unroll
+            for (int rs = 0; rs < 9; ++rs) {
+                const int r = rs / 3, s = rs - r * 3;
+                const uint32_t a_base = tile_addr +
+                    2u * (uint32_t)(((warp * STRIDE + r) * Cfg::IW + a_pix * STRIDE + s) * Cfg::PIXP + a_kof);
+#pragma unroll
+                for (int kc = 0; kc < CIN / 16; ++kc) {
+                    uint32_t a[4];
+                    ldmatrix_x4(a, a_base + kc * 32);
+                    const int q = rs * (CIN / 16) + kc;
+                    mma16816(acc[0], a, breg[q][0], breg[q][1]);
+                    mma16816(acc[1], a, breg[q][2], breg[q][3]);
+                }
+            }
+        } else {
 #pragma unroll 1
         for (int rs = 0; rs < 9; ++rs) {
             const int r = rs / 3, s = rs - r * 3;
@@ -130,6 +153,7 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
                     mma16816(acc[2 * nc + 1], a, b[2], b[3]);
                 }
             }
+        }
         }
 
         // ---- epilogue ----

@@ -161,7 +161,7 @@ static int launch_conv3(const __half* in, __half* out, const __half* w1, const f
     if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv3x3: stride-2 input must be even");
 #define C3CASE(CI, CM, S, CP, R, MB) \
     if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0)) return launch_conv3_t<CI, CM, S, CP, R, MB>(p, st);
-    C3CASE(32, 16, 1, 0, false, 4)      // blocks.0.0  ConvBnAct
+    C3CASE(32, 16, 1, 0, false, 2)      // blocks.0.0  ConvBnAct (weights in registers)
     C3CASE(16, 64, 2, 32, false, 2)     // blocks.1.0  EdgeResidual s2
     C3CASE(32, 128, 1, 32, true, 1)     // blocks.1.1
     C3CASE(32, 128, 2, 48, false, 1)    // blocks.2.0
