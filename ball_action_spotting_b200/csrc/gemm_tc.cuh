@@ -22,22 +22,30 @@ namespace mds {
 
 struct TcGemmParams {
     __half* C;            // [M][N]
-    long long M;
+    const __half* res;    // [M][N] residual added in fp32 before the rounding, or nullptr
+    long long M;          // total rows
+    int rows_per_img;     // streamed mode: M tiles never straddle images (B differs per image)
+    int tiles_per_img;
     int N, K, BN;
     int act;
     int m_tiles, n_tiles;
-    int stages;           // W ring depth
+    int stages;           // ring depth
     int tmem_cols;        // power of two >= 2*BN
+    int streamed;         // 0: A row tile resident in smem, swept over all N tiles (K <= 192)
+                          // 1: A streamed with B through the ring (any K), one N tile, B = per-image gated weights
 };
 
 constexpr int kTcBM = 128, kTcBK = 64, kTcMaxKB = 3;
 constexpr int kTcEpiWarps = 16;
+constexpr int kGP = 3;                 // 16-column groups an epilogue warp holds in registers at once
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 constexpr int kTcABytes = kTcBM * kTcBK * 2;          // 16 KB per K block
 
-__host__ __device__ inline int tc_stages(int BN) { return BN > 192 ? 3 : 4; }
-__host__ __device__ inline size_t tc_smem_bytes(int BN) {
-    return 1024 /*align slack*/ + (size_t)(2 * kTcMaxKB + 1) * kTcABytes + (size_t)tc_stages(BN) * BN * 128 + 256 /*barriers*/;
+__host__ __device__ inline int tc_stages(int BN, int streamed) { return streamed ? 4 : (BN > 192 ? 3 : 4); }
+__host__ __device__ inline size_t tc_smem_bytes(int BN, int streamed) {
+    const size_t ring = streamed ? (size_t)tc_stages(BN, 1) * (kTcABytes + (size_t)BN * 128)
+                                 : (size_t)2 * kTcMaxKB * kTcABytes + (size_t)tc_stages(BN, 0) * BN * 128;
+    return 1024 /*align slack*/ + kTcABytes /*ones tile*/ + ring + 256 /*barriers*/;
 }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------
@@ -71,6 +79,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* ptr, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(ptr));
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -120,11 +139,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ unsigned char tc_smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* s_a = smem;                                           // [2][kTcMaxKB][16 KB]
-    unsigned char* s_ones = smem + (size_t)2 * kTcMaxKB * kTcABytes;     // 128x64 tile: columns 0,1 = 1.0, rest 0
-    unsigned char* s_b = s_ones + kTcABytes;                             // [stages][BN * 128 B]
     const int b_bytes = p.BN * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + (size_t)p.stages * b_bytes);
+    unsigned char* s_ones = smem;                                        // 128x64 tile: columns 0,1 = 1.0, rest 0
+    unsigned char* s_a = s_ones + kTcABytes;                             // resident mode: [2][kTcMaxKB][16 KB]
+    unsigned char* s_ring = p.streamed ? s_ones + kTcABytes : s_a + (size_t)2 * kTcMaxKB * kTcABytes;
+    const int stage_bytes = p.streamed ? kTcABytes + b_bytes : b_bytes; // streamed: [A block | W block], resident: [W block]
+    const int b_off = p.streamed ? kTcABytes : 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)p.stages * stage_bytes);
     uint64_t* b_full = bars;                  // [4]
     uint64_t* b_empty = bars + 4;             // [4]
     uint64_t* a_full = bars + 8;              // [2]
@@ -167,26 +188,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            auto load_a = [&](int i, int mt) {      // A row tile i of this CTA -> buffer i & 1
-                const int ab = i & 1;
-                mbar_wait(&a_empty[ab], (((uint32_t)i >> 1) & 1) ^ 1);
-                mbar_expect_tx(&a_full[ab], (uint32_t)(num_kb * kTcABytes));
-                for (int kb = 0; kb < num_kb; ++kb)
-                    tma_load_2d(s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes, &tmA, &a_full[ab], kb * kTcBK, mt * kTcBM);
-            };
-            int i = 0;
-            if ((int)blockIdx.x < p.m_tiles) load_a(0, blockIdx.x);
-            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++i) {
-                // the next row tile's A is requested a whole tile ahead, so its HBM latency hides behind this tile
-                if (mt + (int)gridDim.x < p.m_tiles) load_a(i + 1, mt + gridDim.x);
-                for (int nt = 0; nt < p.n_tiles; ++nt)
+            if (p.streamed) {
+                for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+                    const int img = mt / p.tiles_per_img, ti = mt - img * p.tiles_per_img;
+                    const int row0 = img * p.rows_per_img + ti * kTcBM;
                     for (int kb = 0; kb <= num_kb; ++kb) {              // block num_kb = the bias block
                         mbar_wait(&b_empty[stage], phase ^ 1);
-                        mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
-                        if (kb < num_kb) tma_load_2d(s_b + (size_t)stage * b_bytes, &tmB, &b_full[stage], kb * kTcBK, nt * p.BN);
-                        else tma_load_2d(s_b + (size_t)stage * b_bytes, &tmBias, &b_full[stage], 0, nt * p.BN);
+                        unsigned char* st = s_ring + (size_t)stage * stage_bytes;
+                        if (kb < num_kb) {
+                            mbar_expect_tx(&b_full[stage], (uint32_t)(kTcABytes + b_bytes));
+                            tma_load_2d(st, &tmA, &b_full[stage], kb * kTcBK, row0);
+                            tma_load_3d(st + b_off, &tmB, &b_full[stage], kb * kTcBK, 0, img);
+                        } else {
+                            mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
+                            tma_load_2d(st + b_off, &tmBias, &b_full[stage], 0, 0);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
+                }
+            } else {
+                auto load_a = [&](int i, int mt) {      // A row tile i of this CTA -> buffer i & 1
+                    const int ab = i & 1;
+                    mbar_wait(&a_empty[ab], (((uint32_t)i >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&a_full[ab], (uint32_t)(num_kb * kTcABytes));
+                    for (int kb = 0; kb < num_kb; ++kb)
+                        tma_load_2d(s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes, &tmA, &a_full[ab], kb * kTcBK, mt * kTcBM);
+                };
+                int i = 0;
+                if ((int)blockIdx.x < p.m_tiles) load_a(0, blockIdx.x);
+                for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++i) {
+                    // the next row tile's A is requested a whole tile ahead, so its HBM latency hides behind this tile
+                    if (mt + (int)gridDim.x < p.m_tiles) load_a(i + 1, mt + gridDim.x);
+                    for (int nt = 0; nt < p.n_tiles; ++nt)
+                        for (int kb = 0; kb <= num_kb; ++kb) {              // block num_kb = the bias block
+                            mbar_wait(&b_empty[stage], phase ^ 1);
+                            mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
+                            if (kb < num_kb) tma_load_2d(s_ring + (size_t)stage * stage_bytes, &tmB, &b_full[stage], kb * kTcBK, nt * p.BN);
+                            else tma_load_2d(s_ring + (size_t)stage * stage_bytes, &tmBias, &b_full[stage], 0, nt * p.BN);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                }
             }
         }
     } else if (warp == 1) {
@@ -198,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int i = 0, t = 0;
             for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x, ++i) {
                 const int ab = i & 1;
-                mbar_wait(&a_full[ab], ((uint32_t)i >> 1) & 1);
+                if (!p.streamed) mbar_wait(&a_full[ab], ((uint32_t)i >> 1) & 1);
                 for (int nt = 0; nt < p.n_tiles; ++nt, ++t) {
                     const int acc = t & 1;
                     mbar_wait(&acc_empty[acc], (((uint32_t)t >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
@@ -208,17 +249,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mbar_wait(&b_full[stage], phase);
                         tc_fence_after();
                         const bool bias_blk = kb == num_kb;
-                        const uint64_t adesc = tc_smem_desc(smem_u32(bias_blk ? s_ones : s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes));
-                        const uint64_t bdesc = tc_smem_desc(smem_u32(s_b + (size_t)stage * b_bytes));
+                        unsigned char* st = s_ring + (size_t)stage * stage_bytes;
+                        const unsigned char* a_src = bias_blk ? s_ones : (p.streamed ? st : s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes);
+                        const uint64_t adesc = tc_smem_desc(smem_u32(a_src));
+                        const uint64_t bdesc = tc_smem_desc(smem_u32(st + b_off));
                         const int nk = bias_blk ? 1 : kTcBK / 16;       // the bias block only has K = 16 worth of data
                         for (int k = 0; k < nk; ++k)     // advance 16 K-elements = 32 B inside the swizzle atom (>>4 = 2)
                             tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                        tc_commit(&b_empty[stage]);                  // W stage reusable once these MMAs have read it
+                        tc_commit(&b_empty[stage]);                  // stage reusable once these MMAs have read it
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                     tc_commit(&acc_full[acc]);                       // accumulator complete
                 }
-                tc_commit(&a_empty[ab]);                             // every MMA that reads this A tile has been issued
+                if (!p.streamed) tc_commit(&a_empty[ab]);            // every MMA that reads this A tile has been issued
             }
         }
     } else {
@@ -232,31 +275,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ngroups = p.BN >> 4;
         int t = 0;
         for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-            const long long row = (long long)mt * kTcBM + q * 32 + lane;
-            const bool row_ok = row < p.M;
+            long long row;
+            bool row_ok;
+            if (p.streamed) {
+                const int img = mt / p.tiles_per_img, ti = mt - img * p.tiles_per_img;
+                const int r_in = ti * kTcBM + q * 32 + lane;
+                row_ok = r_in < p.rows_per_img;
+                row = (long long)img * p.rows_per_img + r_in;
+            } else {
+                row = (long long)mt * kTcBM + q * 32 + lane;
+                row_ok = row < p.M;
+            }
             __half* c_row = p.C + row * p.N;
+            const __half* r_row = p.res + row * p.N;
             for (int nt = 0; nt < p.n_tiles; ++nt, ++t) {
                 if ((t & 1) != e) continue;
-                mbar_wait(&acc_full[e], ((uint32_t)t >> 1) & 1);
-                tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e * p.BN);
                 const int n0 = nt * p.BN;
-                for (int g0 = half; g0 < ngroups; g0 += 8) {       // up to 4 column groups (64 accumulator columns) per pass
-                    uint32_t v[4][16];
+                const bool has_res = p.res != nullptr;
+                for (int g0 = half; g0 < ngroups; g0 += 2 * kGP) {   // up to kGP column groups (48 accumulator columns) per pass
+                    uint32_t rv[kGP][8];
+                    if (has_res) {       // residual loads are issued before waiting for the accumulator
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < kGP; ++j) {
+                            const int g = g0 + 2 * j;
+                            if (g < ngroups && row_ok) ld_global_v8(r_row + n0 + g * 16, rv[j]);
+                        }
+                    }
+                    if (g0 == half) {
+                        mbar_wait(&acc_full[e], ((uint32_t)t >> 1) & 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e * p.BN);
+                    uint32_t v[kGP][16];
+#pragma unroll
+                    for (int j = 0; j < kGP; ++j) {
                         const int g = g0 + 2 * j;
                         if (g < ngroups) tc_ld16(t_row + (uint32_t)(g * 16), v[j]);
                     }
                     tc_wait_ld();
-                    if (g0 + 8 >= ngroups) {
+                    if (g0 + 2 * kGP >= ngroups) {
                         // last TMEM read of this tile: hand the accumulator back before doing the math / stores
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[e]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < kGP; ++j) {
                         const int g = g0 + 2 * j;
                         if (g < ngroups) {
                             uint32_t pk[8];
@@ -265,6 +329,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 float x0 = __uint_as_float(v[j][4 * h]), x1 = __uint_as_float(v[j][4 * h + 1]);
                                 float x2 = __uint_as_float(v[j][4 * h + 2]), x3 = __uint_as_float(v[j][4 * h + 3]);
                                 if (p.act) { x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3); }
+                                if (has_res && row_ok) {
+                                    const float2 r01 = unpack_half2(rv[j][2 * h]), r23 = unpack_half2(rv[j][2 * h + 1]);
+                                    x0 += r01.x; x1 += r01.y; x2 += r23.x; x3 += r23.y;
+                                }
                                 pk[2 * h] = pack_half2(x0, x1);
                                 pk[2 * h + 1] = pack_half2(x2, x3);
                             }

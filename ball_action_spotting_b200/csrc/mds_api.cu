@@ -216,6 +216,21 @@ static int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int K
     return MDS_OK;
 }
 
+// per-image gated weights [n_img][N][K] fp16: box = 64 (K) x BN x 1
+static int make_tmap_3d(CUtensorMap* map, const void* ptr, int n_img, int N, int K, int box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)n_img};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) n=%d N=%d K=%d", (int)r, n_img, N, K);
+    return MDS_OK;
+}
+
 static int tc_pick_bn(int N) {
     if (N <= 256) return N;
     const int cand[] = {256, 224, 192, 160, 128, 112, 96, 64};
@@ -223,23 +238,13 @@ static int tc_pick_bn(int N) {
     return 0;
 }
 
-static int launch_gemm_tc(const __half* A, const __half* W, const __half* bias_mat, __half* C, long long M, int N, int K, int act,
-                          cudaStream_t st) {
-    const int BN = tc_pick_bn(N);
-    if (BN < 32 || BN % 16 || K > kTcMaxKB * kTcBK) return fail(MDS_ERR_INVALID, "gemm_tc: unsupported N=%d K=%d", N, K);
-    CUtensorMap tmA, tmB, tmBias;
-    TRY(make_tmap_2d(&tmA, A, M, K, kTcBM));
-    TRY(make_tmap_2d(&tmB, W, N, K, BN));
-    TRY(make_tmap_2d(&tmBias, bias_mat, N, kTcBK, BN));
-    TcGemmParams p;
-    p.C = C; p.M = M; p.N = N; p.K = K; p.BN = BN; p.act = act;
-    p.m_tiles = (int)((M + kTcBM - 1) / kTcBM);
-    p.n_tiles = N / BN;
-    p.stages = tc_stages(BN);
+static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBias, TcGemmParams& p, cudaStream_t st) {
     int cols = 32;
-    while (cols < 2 * BN) cols <<= 1;
+    while (cols < 2 * p.BN) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t smem = tc_smem_bytes(BN);
+    p.stages = tc_stages(p.BN, p.streamed);
+    const size_t smem = tc_smem_bytes(p.BN, p.streamed);
+    if (smem > 227 * 1024) return fail(MDS_ERR_INVALID, "gemm_tc: BN=%d needs %zu bytes of shared memory", p.BN, smem);
     static size_t smem_set = 0;
     if (smem > smem_set) {
         CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -251,6 +256,42 @@ static int launch_gemm_tc(const __half* A, const __half* W, const __half* bias_m
     gemm_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, tmBias, p);
     LAUNCH_CHECK("gemm_tc");
     return MDS_OK;
+}
+
+// resident-A mode: C = act(A W^T + bias), K <= 192, all N tiles swept per row tile
+static int launch_gemm_tc(const __half* A, const __half* W, const __half* bias_mat, __half* C, long long M, int N, int K, int act,
+                          cudaStream_t st) {
+    const int BN = tc_pick_bn(N);
+    if (BN < 32 || BN % 16 || K > kTcMaxKB * kTcBK) return fail(MDS_ERR_INVALID, "gemm_tc: unsupported N=%d K=%d", N, K);
+    CUtensorMap tmA, tmB, tmBias;
+    TRY(make_tmap_2d(&tmA, A, M, K, kTcBM));
+    TRY(make_tmap_2d(&tmB, W, N, K, BN));
+    TRY(make_tmap_2d(&tmBias, bias_mat, N, kTcBK, BN));
+    TcGemmParams p;
+    p.C = C; p.res = nullptr; p.M = M; p.rows_per_img = (int)M; p.tiles_per_img = (int)((M + kTcBM - 1) / kTcBM);
+    p.N = N; p.K = K; p.BN = BN; p.act = act; p.streamed = 0;
+    p.m_tiles = p.tiles_per_img;
+    p.n_tiles = N / BN;
+    return tc_launch(tmA, tmB, tmBias, p, st);
+}
+
+// streamed mode: C[img] = act(A[img] Wg[img]^T + bias) (+ res); Wg = per-image SE-gated weights written by se_fc_kernel
+static int launch_gemm_tc_stream(const __half* A, const __half* Wg, const __half* bias_mat, const __half* res, __half* C,
+                                 int rows_per_img, int n_img, int N, int K, int act, cudaStream_t st) {
+    if (N < 32 || N > 256 || N % 16 || K % 16) return fail(MDS_ERR_INVALID, "gemm_tc_stream: unsupported N=%d K=%d", N, K);
+    if (rows_per_img <= 0 || n_img <= 0) return MDS_OK;
+    const long long M = (long long)rows_per_img * n_img;
+    if (M >= (1LL << 31)) return fail(MDS_ERR_INVALID, "gemm_tc_stream: too many rows");
+    CUtensorMap tmA, tmB, tmBias;
+    TRY(make_tmap_2d(&tmA, A, M, K, kTcBM));
+    TRY(make_tmap_3d(&tmB, Wg, n_img, N, K, N));
+    TRY(make_tmap_2d(&tmBias, bias_mat, N, kTcBK, N));
+    TcGemmParams p;
+    p.C = C; p.res = res; p.M = M; p.rows_per_img = rows_per_img; p.tiles_per_img = (rows_per_img + kTcBM - 1) / kTcBM;
+    p.N = N; p.K = K; p.BN = N; p.act = act; p.streamed = 1;
+    p.m_tiles = p.tiles_per_img * n_img;
+    p.n_tiles = 1;
+    return tc_launch(tmA, tmB, tmBias, p, st);
 }
 
 // bias_mat: [N][64] fp16, column 0 = fp16(bias), column 1 = fp16(bias - column 0), rest 0 (packer.py); enables the tcgen05 path
@@ -335,14 +376,18 @@ static int launch_dw(const __half* in, __half* out, const float* w, const float*
     return launch_dw_t<1, 2>(p, grid, st);
 }
 
-static int launch_se(float* sums, const float* w1, const float* b1, const float* w2t, const float* b2, __half* gate,
-                     int n, int C, int rd, float inv_count, cudaStream_t st) {
+static int launch_se(const float* sums, float* sums_next, const float* w1, const float* b1, const float* w2t, const float* b2,
+                     __half* gate, const float* w32, __half* wg, int n, int C, int rd, int N, float inv_count, cudaStream_t st) {
     if (n <= 0) return MDS_OK;
-    if (C > 4096 || rd > 256 || C % 4) return fail(MDS_ERR_INVALID, "se_fc: C must be a multiple of 4, C <= 4096, rd <= 256");
+    if (C > 4096 || rd > 256 || C % 8) return fail(MDS_ERR_INVALID, "se_fc: C must be a multiple of 8, C <= 4096, rd <= 256");
+    if (n > 65535) return fail(MDS_ERR_INVALID, "se_fc: n too large");
     SeParams p;
-    p.sums = sums; p.w1 = w1; p.b1 = b1; p.w2t = w2t; p.b2 = b2; p.gate = gate; p.C = C; p.rd = rd; p.inv_count = inv_count;
+    p.sums = sums; p.sums_next = sums_next; p.w1 = w1; p.b1 = b1; p.w2t = w2t; p.b2 = b2; p.gate = gate;
+    p.w32 = w32; p.wg = (w32 != nullptr) ? wg : nullptr; p.C = C; p.rd = rd; p.N = N; p.inv_count = inv_count;
+    const int gps = ((C >> 3) + kSeSlices - 1) / kSeSlices;
+    const size_t smem = (size_t)(C + ((rd + 3) & ~3) + gps * 8) * sizeof(float);
     ProfScope ps(MDS_KIND_SE_FC, st);
-    se_fc_kernel<<<n, kSeThreads, (size_t)(C + rd) * sizeof(float), st>>>(p);
+    se_fc_kernel<<<dim3(n, kSeSlices), kSeThreads, smem, st>>>(p);
     LAUNCH_CHECK("se_fc");
     return MDS_OK;
 }
@@ -379,13 +424,13 @@ struct Block2d {
     char kind;   // 'c' ConvBnAct, 'e' EdgeResidual, 'i' InvertedResidual
     int cin, mid, cout, stride, rd;
     bool skip;
-    const __half *w1 = nullptr, *w2 = nullptr, *wpw = nullptr, *wpwl = nullptr, *bmpw = nullptr;
+    const __half *w1 = nullptr, *w2 = nullptr, *wpw = nullptr, *wpwl = nullptr, *bmpw = nullptr, *bmpwl = nullptr;
     const float *b1 = nullptr, *b2 = nullptr, *bpw = nullptr, *bpwl = nullptr;
-    const float *wdw = nullptr, *bdw = nullptr, *se_w1 = nullptr, *se_b1 = nullptr, *se_w2t = nullptr, *se_b2 = nullptr;
+    const float *wdw = nullptr, *bdw = nullptr, *se_w1 = nullptr, *se_b1 = nullptr, *se_w2t = nullptr, *se_b2 = nullptr, *w32pwl = nullptr;
 };
 struct Block3d {
-    const __half *wpw, *wpwl, *bmpw;
-    const float *bpw, *bpwl, *wdw, *bdw, *se_w1, *se_b1, *se_w2t, *se_b2;
+    const __half *wpw, *wpwl, *bmpw, *bmpwl;
+    const float *bpw, *bpwl, *wdw, *bdw, *se_w1, *se_b1, *se_w2t, *se_b2, *w32pwl;
 };
 
 struct MdsHandle {
@@ -510,6 +555,8 @@ extern "C" int mds_weights_commit(MdsHandle* h) {
                 TRY(get_tensor(h, p + "se.b2", b.mid, &b.se_b2));
                 TRY(get_tensor(h, p + "pwl.w", (size_t)b.cout * b.mid, &b.wpwl));
                 TRY(get_tensor(h, p + "pwl.b", b.cout, &b.bpwl));
+                TRY(get_tensor(h, p + "pwl.w32", (size_t)b.cout * b.mid, &b.w32pwl));
+                TRY(get_tensor(h, p + "pwl.bm", (size_t)b.cout * 64, &b.bmpwl));
             }
             h->blocks.push_back(b);
             cin = b.cout;
@@ -535,6 +582,8 @@ extern "C" int mds_weights_commit(MdsHandle* h) {
         TRY(get_tensor(h, p + "se.b2", mid, &b.se_b2));
         TRY(get_tensor(h, p + "pwl.w", (size_t)c3 * mid, &b.wpwl));
         TRY(get_tensor(h, p + "pwl.b", c3, &b.bpwl));
+        TRY(get_tensor(h, p + "pwl.w32", (size_t)c3 * mid, &b.w32pwl));
+        TRY(get_tensor(h, p + "pwl.bm", (size_t)c3 * 64, &b.bmpwl));
         h->blocks3d.push_back(b);
     }
     TRY(get_tensor(h, "proj3d.w", (size_t)pj * c3, &h->proj3d_w));
@@ -594,17 +643,19 @@ static Sizes2d sizes2d(int H, int W) {
     return s;
 }
 
+constexpr size_t kMaxGatedW = 192 * 1152;   // largest encoder projection (blocks.5.x conv_pwl)
 static size_t ws2d_bytes(const MdsHandle* h, int H, int W, int n_images) {
     int cs = n_images < h->cfg.chunk_images ? n_images : h->cfg.chunk_images;
     if (cs <= 0) cs = 1;
     Sizes2d s = sizes2d(H, W);
     return 2 * al256(s.stream_elems * cs * 2) + al256(s.mid1_elems * cs * 2) + al256(s.mid2_elems * cs * 2) +
-           al256((size_t)cs * 1152 * 4) + al256((size_t)cs * 1152 * 2);
+           2 * al256((size_t)cs * 1152 * 4) + al256((size_t)cs * 1152 * 2) + al256((size_t)cs * kMaxGatedW * 2);
 }
 static size_t ws3d_bytes(const MdsHandle* h, int b, int P) {
     const size_t rows = (size_t)b * h->T() * P;
     return 2 * al256(rows * h->cfg.num_3d_features * 2) + 2 * al256(rows * h->mid3d() * 2) +
-           al256((size_t)b * h->mid3d() * 4) + al256((size_t)b * h->mid3d() * 2);
+           2 * al256((size_t)b * h->mid3d() * 4) + al256((size_t)b * h->mid3d() * 2) +
+           al256((size_t)b * h->cfg.num_3d_features * h->mid3d() * 2);
 }
 static size_t wshead_bytes(const MdsHandle* h, int b) { return al256((size_t)b * h->cfg.num_3d_stack_proj * h->T() * 4); }
 
@@ -639,10 +690,16 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
     X[1] = ar.take<__half>(sz.stream_elems * cs_max);
     __half* M1 = ar.take<__half>(sz.mid1_elems * cs_max);
     __half* M2 = ar.take<__half>(sz.mid2_elems * cs_max);
-    float* sums = ar.take<float>((size_t)cs_max * 1152);
+    float* sums2[2];
+    sums2[0] = ar.take<float>((size_t)cs_max * 1152);
+    sums2[1] = ar.take<float>((size_t)cs_max * 1152);
     __half* gate = ar.take<__half>((size_t)cs_max * 1152);
+    __half* wg = ar.take<__half>((size_t)cs_max * kMaxGatedW);
     if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_2d: workspace too small");
-    CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)cs_max * 1152 * sizeof(float), st));
+    // SE squeeze sums ping-pong between two buffers: layer i accumulates into sums2[i & 1] (pre-cleared by the SE kernel
+    // of layer i-1).  Both start cleared.  Buffers are laid out [image][C of that layer].
+    CUDA_TRY(cudaMemsetAsync(sums2[0], 0, 2 * al256((size_t)cs_max * 1152 * sizeof(float)), st));
+    int se_layer = 0;
     const int elem = fr.dtype == 0 ? 1 : 4;
     const int P = (fr.H / 32) * (fr.W / 32);
 
@@ -662,9 +719,13 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
                 TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, b.w2, b.b2, cs, hh, ww, b.cin, b.mid, b.stride, b.cout, b.skip, st));
             } else {
                 TRY(launch_gemm(X[cur], b.wpw, b.bpw, nullptr, nullptr, M1, (long long)hh * ww, cs, b.mid, b.cin, 1, st, b.bmpw));
+                float* sums = sums2[se_layer & 1];
+                float* sums_next = sums2[(se_layer + 1) & 1];
+                ++se_layer;
                 TRY(launch_dw(M1, M2, b.wdw, b.bdw, sums, cs, 1, hh, ww, b.mid, 1, b.stride, st));
-                TRY(launch_se(sums, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, cs, b.mid, b.rd, 1.0f / (float)(ho * wo), st));
-                TRY(launch_gemm(M2, b.wpwl, b.bpwl, b.skip ? X[cur] : nullptr, gate, X[cur ^ 1], (long long)ho * wo, cs, b.cout, b.mid, 0, st));
+                TRY(launch_se(sums, sums_next, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, b.w32pwl, wg, cs, b.mid, b.rd, b.cout,
+                              1.0f / (float)(ho * wo), st));
+                TRY(launch_gemm_tc_stream(M2, wg, b.bmpwl, b.skip ? X[cur] : nullptr, X[cur ^ 1], ho * wo, cs, b.cout, b.mid, 0, st));
             }
             cur ^= 1; hh = ho; ww = wo;
         }
@@ -686,10 +747,14 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
     Y[1] = ar.take<__half>(rows * c3);
     __half* M1 = ar.take<__half>(rows * mid);
     __half* M2 = ar.take<__half>(rows * mid);
-    float* sums = ar.take<float>((size_t)b * mid);
+    float* sums2[2];
+    sums2[0] = ar.take<float>((size_t)b * mid);
+    sums2[1] = ar.take<float>((size_t)b * mid);
     __half* gate = ar.take<__half>((size_t)b * mid);
+    __half* wg = ar.take<__half>((size_t)b * c3 * mid);
     if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_3d: workspace too small");
-    CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)b * mid * sizeof(float), st));
+    CUDA_TRY(cudaMemsetAsync(sums2[0], 0, 2 * al256((size_t)b * mid * sizeof(float)), st));
+    int se_layer = 0;
     const __half* x = feats;
     int nxt = 0;
     // the 2D features are [b][T][h][w][C] already, i.e. the reference's transpose(1,2) is a no-op in NDHWC
@@ -698,9 +763,13 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
     for (const Block3d& blk : h->blocks3d) {
         ++g_prof_tag;
         TRY(launch_gemm(x, blk.wpw, blk.bpw, nullptr, nullptr, M1, (long long)T * P, b, mid, c3, 1, st, blk.bmpw));
+        float* sums = sums2[se_layer & 1];
+        float* sums_next = sums2[(se_layer + 1) & 1];
+        ++se_layer;
         TRY(launch_dw(M1, M2, blk.wdw, blk.bdw, sums, b, T, fh, fw, mid, 3, 1, st));
-        TRY(launch_se(sums, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, b, mid, rd, 1.0f / (float)((size_t)T * P), st));
-        TRY(launch_gemm(M2, blk.wpwl, blk.bpwl, x, gate, Y[nxt], (long long)T * P, b, c3, mid, 0, st));
+        TRY(launch_se(sums, sums_next, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, blk.w32pwl, wg, b, mid, rd, c3,
+                      1.0f / (float)((size_t)T * P), st));
+        TRY(launch_gemm_tc_stream(M2, wg, blk.bmpwl, x, Y[nxt], T * P, b, c3, mid, 0, st));
         x = Y[nxt];
         nxt ^= 1;
     }
@@ -814,9 +883,16 @@ extern "C" int mds_k_dwconv(const void* in, void* out, const float* w, const flo
     return launch_dw(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), w, bias, sums, n, T, H, W, C, kt,
                      stride, reinterpret_cast<cudaStream_t>(stream));
 }
-extern "C" int mds_k_se_fc(float* sums, const float* w1, const float* b1, const float* w2t, const float* b2, void* gate, int n,
-                           int C, int rd, float inv_count, void* stream) {
-    return launch_se(sums, w1, b1, w2t, b2, reinterpret_cast<__half*>(gate), n, C, rd, inv_count, reinterpret_cast<cudaStream_t>(stream));
+extern "C" int mds_k_se_fc(const float* sums, float* sums_next, const float* w1, const float* b1, const float* w2t, const float* b2,
+                           void* gate, const float* w32, void* wg, int n, int C, int rd, int N, float inv_count, void* stream) {
+    return launch_se(sums, sums_next, w1, b1, w2t, b2, reinterpret_cast<__half*>(gate), w32, reinterpret_cast<__half*>(wg), n, C,
+                     rd, N, inv_count, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_gemm_gated(const void* A, const void* wg, const void* bias_mat, const void* res, void* C, int rows_per_img,
+                                int n_img, int N, int K, int act, void* stream) {
+    return launch_gemm_tc_stream(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(wg),
+                                 reinterpret_cast<const __half*>(bias_mat), reinterpret_cast<const __half*>(res),
+                                 reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int mds_k_gem(const void* x, float* feat, int b, int T, int P, int C, float p, float eps, void* stream) {
     return launch_gem(reinterpret_cast<const __half*>(x), feat, b, T, P, C, p, eps, reinterpret_cast<cudaStream_t>(stream));

@@ -4,30 +4,38 @@
 
 namespace mds {
 
-// gate[n][c] = sigmoid(W2 . SiLU(W1 . mean + b1) + b2), mean = sums / count.   One CTA per image.
-// Also clears sums[n][:] so the next depthwise layer can accumulate into the same buffer.
+// gate[n][c] = sigmoid(W2 . SiLU(W1 . mean + b1) + b2), mean = sums / count  (timm SqueezeExcite; multidim_stacker.py:86-90).
+// grid = (images, kSeSlices): every CTA recomputes the tiny squeeze FC, then owns one slice of the channels: it writes
+// their gates and — when wg != nullptr — the slice's columns of this image's gated projection weights
+//     wg[n][o][c] = fp16( w32[o][c] * gate[c] )          (fp32 product, ONE rounding)
+// which the tcgen05 projection GEMM consumes through a 3-D tensor map.  Slice 0 also clears `sums_next` (the buffer the
+// next depthwise layer accumulates into; sums ping-pong between two buffers so no CTA clears what another still reads).
 struct SeParams {
-    float* sums;          // [n][C]
+    const float* sums;    // [n][C]
+    float* sums_next;     // [n][C] or nullptr
     const float* w1;      // [rd][C]
     const float* b1;      // [rd]
     const float* w2t;     // [rd][C]  (conv_expand weight transposed)
     const float* b2;      // [C]
     __half* gate;         // [n][C]
-    int C, rd;
+    const float* w32;     // [N][C] folded projection weights (fp32) or nullptr
+    __half* wg;           // [n][N][C] or nullptr
+    int C, rd, N;
     float inv_count;
 };
 
-constexpr int kSeThreads = 1024;
+constexpr int kSeThreads = 512;
+constexpr int kSeSlices = 8;
 __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
     extern __shared__ float s_se[];
     float* s_mean = s_se;            // [C]
     float* s_hid = s_se + p.C;       // [rd]
-    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* sums = p.sums + (size_t)n * p.C;
-    for (int c = tid; c < p.C; c += kSeThreads) {
-        s_mean[c] = sums[c] * p.inv_count;
-        sums[c] = 0.f;
-    }
+    float* s_gate = s_hid + ((p.rd + 3) & ~3);   // [slice width]
+    const int n = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* sums = p.sums + (size_t)n * p.C;
+    for (int c = tid; c < p.C; c += kSeThreads) s_mean[c] = sums[c] * p.inv_count;
+    if (slice == 0 && p.sums_next != nullptr)
+        for (int c = tid; c < p.C; c += kSeThreads) p.sums_next[(size_t)n * p.C + c] = 0.f;
     __syncthreads();
     // squeeze FC: one hidden unit per warp pass, 4 independent partial sums per lane so the loads overlap
     for (int j = warp; j < p.rd; j += kSeThreads / 32) {
@@ -43,7 +51,10 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
         if (lane == 0) s_hid[j] = silu_f(acc + __ldg(p.b1 + j));
     }
     __syncthreads();
-    for (int c = tid; c < p.C; c += kSeThreads) {
+    // this CTA's channel slice, in units of 8 channels (16 bytes of fp16)
+    const int groups = p.C >> 3, gps = (groups + kSeSlices - 1) / kSeSlices;
+    const int c_lo = min(p.C, slice * gps * 8), c_hi = min(p.C, c_lo + gps * 8);
+    for (int c = c_lo + tid; c < c_hi; c += kSeThreads) {
         float a0 = __ldg(p.b2 + c), a1 = 0.f;
         int j = 0;
 #pragma unroll 4
@@ -52,7 +63,24 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
             a1 = fmaf(__ldg(p.w2t + (size_t)(j + 1) * p.C + c), s_hid[j + 1], a1);
         }
         if (j < p.rd) a0 = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], a0);
-        p.gate[(size_t)n * p.C + c] = __float2half_rn(sigmoid_f(a0 + a1));
+        const float gv = sigmoid_f(a0 + a1);
+        s_gate[c - c_lo] = gv;
+        p.gate[(size_t)n * p.C + c] = __float2half_rn(gv);
+    }
+    if (p.wg == nullptr) return;
+    __syncthreads();
+    const int wgrp = (c_hi - c_lo) >> 3;                 // 8-channel groups in this slice
+    __half* wg = p.wg + (size_t)n * p.N * p.C;
+    for (int i = tid; i < p.N * wgrp; i += kSeThreads) {
+        const int o = i / wgrp, gq = i - o * wgrp;
+        const int c = c_lo + gq * 8;
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.w32 + (size_t)o * p.C + c));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(p.w32 + (size_t)o * p.C + c + 4));
+        const float* gp = s_gate + gq * 8;
+        uint4 v;
+        v.x = pack_half2(x0.x * gp[0], x0.y * gp[1]); v.y = pack_half2(x0.z * gp[2], x0.w * gp[3]);
+        v.z = pack_half2(x1.x * gp[4], x1.y * gp[5]); v.w = pack_half2(x1.z * gp[6], x1.w * gp[7]);
+        *reinterpret_cast<uint4*>(wg + (size_t)o * p.C + c) = v;
     }
 }
 

@@ -68,12 +68,14 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str
         out[name + ".w"] = _h(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))   # [co][(r*3+s)*ci + c]
         out[name + ".b"] = _f(b)
 
-    def pw(name, wkey, bn, eps, bias_mat=False):
+    def pw(name, wkey, bn, eps, bias_mat=False, gated=False):
         w, b = _fold(sd, wkey, bn, eps)
         out[name + ".w"] = _h(w.reshape(w.shape[0], w.shape[1]))            # [co][ci]
         out[name + ".b"] = _f(b)
-        if bias_mat:
+        if bias_mat or gated:
             out[name + ".bm"] = bias_matrix(b)
+        if gated:       # SE-gated projection: the SE kernel multiplies these fp32 weights by the gate, one rounding to fp16
+            out[name + ".w32"] = _f(w.reshape(w.shape[0], w.shape[1]))
 
     def dw(name, wkey, bn, eps):
         w, b = _fold(sd, wkey, bn, eps)                                    # [C][1][(kt)][3][3]
@@ -99,7 +101,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str
                 pw(n + ".pw", p + "conv_pw.weight", p + "bn1", ENC_EPS, bias_mat=True)
                 dw(n + ".dw", p + "conv_dw.weight", p + "bn2", ENC_EPS)
                 se(n + ".se", p + "se")
-                pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3", ENC_EPS)
+                pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3", ENC_EPS, gated=True)
 
     pw("proj2d", "conv2d_projection.0.weight", "conv2d_projection.1", REF_EPS, bias_mat=True)
     for i in range(num_3d_blocks):
@@ -107,7 +109,7 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str
         pw(n + ".pw", p + "conv_pw.weight", p + "bn1.bn3d", REF_EPS, bias_mat=True)
         dw(n + ".dw", p + "conv_dw.weight", p + "bn2.bn3d", REF_EPS)
         se(n + ".se", p + "se")
-        pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3.bn3d", REF_EPS)
+        pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3.bn3d", REF_EPS, gated=True)
     pw("proj3d", "conv3d_projection.0.weight", "conv3d_projection.1", REF_EPS, bias_mat=True)
     out["gem.p"] = _f(sd["global_pool.p"].detach().cpu().reshape(1))
     out["cls.w"] = _f(sd["classifier.weight"].detach().cpu())

@@ -181,23 +181,63 @@ def test_dwconv3d_and_se_sums(lib, T):
     assert rel(sums, y.sum((2, 3, 4))) <= 1e-4
 
 
-@pytest.mark.parametrize("C_,rd", [(672, 28), (576, 24), (1152, 48), (192, 12)])
-def test_se_fc(lib, C_, rd):
+@pytest.mark.parametrize("C_,rd,N", [(672, 28, 112), (576, 24, 192), (1152, 48, 192), (192, 12, 96), (384, 24, 96)])
+def test_se_fc_gate_and_gated_weights(lib, C_, rd, N):
     n, count = 3, 920
     sums = torch.randn(n, C_, generator=gen(1)) * count * 0.3
     w1 = torch.randn(rd, C_, generator=gen(2)) * (2.0 / rd) ** 0.5 * 0.2
     b1 = torch.randn(rd, generator=gen(3)) * 0.1
     w2 = torch.randn(C_, rd, generator=gen(4)) * (2.0 / C_) ** 0.5
     b2 = torch.randn(C_, generator=gen(5)) * 0.1
+    w32 = torch.randn(N, C_, generator=gen(6)) * (1.0 / C_) ** 0.5
     mean = sums / count
     ref = torch.sigmoid(F.silu(mean @ w1.t() + b1) @ w2.t() + b2)
-    d_s, d_w1, d_b1, d_w2t, d_b2 = sums.to(DEV), w1.to(DEV), b1.to(DEV), w2.t().contiguous().to(DEV), b2.to(DEV)
+    ref_wg = w32[None] * ref[:, None, :]                       # (n, N, C): what x*gate followed by conv_pwl multiplies by
+    d_s, d_w1, d_b1, d_w2t, d_b2, d_w32 = sums.to(DEV), w1.to(DEV), b1.to(DEV), w2.t().contiguous().to(DEV), b2.to(DEV), w32.to(DEV)
+    nxt = torch.ones((n, C_), dtype=torch.float32, device=DEV)
     gate = torch.zeros((n, C_), dtype=torch.float16, device=DEV)
-    ok(lib.mds_k_se_fc(d_s.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(), d_w2t.data_ptr(), d_b2.data_ptr(),
-                       gate.data_ptr(), n, C_, rd, 1.0 / count, None), lib)
+    wg = torch.zeros((n, N, C_), dtype=torch.float16, device=DEV)
+    ok(lib.mds_k_se_fc(d_s.data_ptr(), nxt.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(), d_w2t.data_ptr(), d_b2.data_ptr(),
+                       gate.data_ptr(), d_w32.data_ptr(), wg.data_ptr(), n, C_, rd, N, 1.0 / count, None), lib)
     torch.cuda.synchronize()
     assert rel(gate, ref) <= TOL
-    assert float(d_s.abs().max()) == 0.0             # the kernel hands the buffer back zeroed
+    assert rel(wg, ref_wg) <= TOL
+    assert float(nxt.abs().max()) == 0.0             # the next layer's squeeze buffer is handed over cleared
+    assert torch.equal(d_s.cpu(), sums)              # ... and the current one is left untouched
+
+
+GATED_CASES = [(96, 192, 0), (96, 384, 1), (112, 576, 0), (112, 672, 1), (192, 672, 0), (192, 1152, 1), (192, 576, 1)]
+
+
+@pytest.mark.parametrize("N,K,res", GATED_CASES)
+@pytest.mark.parametrize("rows", [150, 920])
+def test_gemm_gated_tcgen05(lib, N, K, res, rows):
+    """conv_pwl(x * gate) + bn3 (+ shortcut) with per-image gated weights, streamed tcgen05 kernel."""
+    from ball_action_spotting_b200.packer import bias_matrix
+    n_img = 3
+    M = rows * n_img
+    A = h16(torch.randn(M, K, generator=gen(1)))
+    w32 = torch.randn(N, K, generator=gen(2)) * (1.0 / K) ** 0.5
+    g = torch.rand(n_img, K, generator=gen(4))
+    wg = h16(w32[None] * g[:, None, :])                                    # what se_fc_kernel writes
+    bias = torch.randn(N, generator=gen(3)) * 0.1
+    y = torch.einsum("imk,ink->imn", A.float().view(n_img, rows, K), wg.float()).reshape(M, N) + bias
+    r = None
+    if res:
+        r = h16(torch.randn(M, N, generator=gen(5)))
+        y = y + r.float()
+    d = lambda t: None if t is None else t.contiguous().to(DEV)
+    dA, dwg, dbm, dr = d(A), d(wg), d(bias_matrix(bias)), d(r)
+    out = torch.zeros((M, N), dtype=torch.float16, device=DEV)
+    ok(lib.mds_k_gemm_gated(dA.data_ptr(), dwg.data_ptr(), dbm.data_ptr(), None if dr is None else dr.data_ptr(), out.data_ptr(),
+                            rows, n_img, N, K, 0, None), lib)
+    torch.cuda.synchronize()
+    assert rel(out, y) <= TOL
+    # against the un-rounded fp32 gated weights (the reference's x * gate then conv): still within the kernel tolerance
+    y32 = torch.einsum("imk,ink->imn", A.float().view(n_img, rows, K), w32[None] * g[:, None, :]).reshape(M, N) + bias
+    if res:
+        y32 = y32 + r.float()
+    assert rel(out, y32) <= TOL
 
 
 @pytest.mark.parametrize("p", [3.0, 2.5])
