@@ -43,6 +43,11 @@ struct DwCfg {
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 lds_half2(uint32_t saddr) {
+    uint32_t u;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(saddr));
+    return unpack_half2(u);
+}
 
 template <int KT, int STRIDE>
 __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
@@ -71,10 +76,12 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     const size_t plane = (size_t)p.H * p.W * p.C;
     const __half* in_n = p.in + (size_t)n * p.T * plane;
 
-    // cp.async bookkeeping that does not depend on the row is computed once per thread
-    int s_off[Cfg::SLOTS];            // halves, inside one row step
-    long long g_off[Cfg::SLOTS];      // elements from in_n for row 0
+    // cp.async bookkeeping that does not depend on the row is computed once per thread; the row-dependent part is a
+    // running pointer, so the steady-state loop has no address arithmetic beyond pointer increments
+    uint32_t s_off[Cfg::SLOTS];       // bytes, inside one row step (smem)
+    const __half* g_ptr[Cfg::SLOTS];  // source of this thread's request for the NEXT row to be issued
     bool s_ok[Cfg::SLOTS];
+    const long long row_pitch = (long long)p.W * p.C;
 #pragma unroll
     for (int sl = 0; sl < Cfg::SLOTS; ++sl) {
         const int idx = tid + sl * 256;
@@ -85,28 +92,31 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
         const int ti = (KT == 3) ? t + pl - 1 : t;
         const int cc = c_slab + c16 * 8;
         s_ok[sl] = (idx < Cfg::CHUNKS) && (xi >= 0) && (xi < p.W) && (ti >= 0) && (ti < p.T) && (cc < p.C);
-        s_off[sl] = pl * Cfg::ROW_HALVES + px * kDwCS + c16 * 8;
-        g_off[sl] = (long long)ti * (long long)plane + (long long)xi * p.C + cc;
-        if (idx >= Cfg::CHUNKS) s_off[sl] = -1;
+        s_off[sl] = (uint32_t)(pl * Cfg::ROW_HALVES + px * kDwCS + c16 * 8) * 2u;
+        g_ptr[sl] = s_ok[sl] ? in_n + (long long)ti * (long long)plane + (long long)yi0 * row_pitch + (long long)xi * p.C + cc : p.in;
+        if (idx >= Cfg::CHUNKS) s_off[sl] = 0xffffffffu;
     }
-    const long long row_pitch = (long long)p.W * p.C;
+    const uint32_t ring_u32 = smem_u32(s_ring);
+    uint32_t iss_off = 0;             // byte offset of the stage the producer side fills next
+    int iss_y = yi0;                  // input row the producer side requests next
 
-    // stage j holds input rows [j*RPS, j*RPS + RPS) of this chunk
-    auto issue = [&](int j) {
-        __half* st = s_ring + (j % Cfg::NST) * Cfg::STAGE_HALVES;
+    auto issue = [&]() {
 #pragma unroll
         for (int rr = 0; rr < Cfg::RPS; ++rr) {
-            const int yi = yi0 + j * Cfg::RPS + rr;
-            const bool yok = (yi >= 0) && (yi < p.H);
-            const __half* row = in_n + (long long)yi * row_pitch;
+            const bool yok = (unsigned)iss_y < (unsigned)p.H;
 #pragma unroll
             for (int sl = 0; sl < Cfg::SLOTS; ++sl) {
-                if (s_off[sl] >= 0) {
+                if (s_off[sl] != 0xffffffffu) {
                     const bool ok = yok && s_ok[sl];
-                    cp_async16(st + rr * Cfg::STEP_HALVES + s_off[sl], ok ? row + g_off[sl] : p.in, ok ? 16 : 0);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ring_u32 + iss_off + rr * (Cfg::STEP_HALVES * 2) + s_off[sl]),
+                                 "l"(ok ? g_ptr[sl] : p.in), "r"(ok ? 16 : 0));
+                    if (s_ok[sl]) g_ptr[sl] += row_pitch;
                 }
             }
+            ++iss_y;
         }
+        iss_off += Cfg::STAGE_HALVES * 2;
+        if (iss_off == Cfg::NST * Cfg::STAGE_HALVES * 2) iss_off = 0;
     };
 
     // per-thread weights: KT*9 taps x 2 channels
@@ -118,7 +128,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     const int NSTG = (NR + Cfg::RPS - 1) / Cfg::RPS;     // stages to stream (rows past NR are loaded but unused)
 #pragma unroll
     for (int j = 0; j < Cfg::NST - 1; ++j) {
-        if (j < NSTG) issue(j);
+        if (j < NSTG) issue();
         cp_async_commit();
     }
 
@@ -130,33 +140,37 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     const int xw = xo0 + warp * kDwPXW;               // first output column of this warp
     const int px_base = (STRIDE == 1) ? warp * kDwPXW : 2 * warp * kDwPXW;
     const long long out_pitch = (long long)p.Wo * p.C;
-    __half* out_base = p.out + ((size_t)n * p.T + t) * (size_t)p.Ho * out_pitch + (long long)xw * p.C + c;
+    // running output pointer: row yo0 of this warp's strip; every emitted row advances it by one output row
+    __half* o_ptr = p.out + ((size_t)n * p.T + t) * (size_t)p.Ho * out_pitch + (long long)yo0 * out_pitch + (long long)xw * p.C + c;
     bool px_ok[kDwPXW];
 #pragma unroll
     for (int j = 0; j < kDwPXW; ++j) px_ok[j] = c_ok && (xw + j < p.Wo);
+    const int pxC = p.C;                             // halves between adjacent output columns
 
-    auto emit = [&](int yo, const float2 (&acc)[kDwPXW]) {
-        __half* row = out_base + (long long)yo * out_pitch;
+    auto emit = [&](const float2 (&acc)[kDwPXW]) {   // rows are emitted in order yo0, yo0+1, ...
 #pragma unroll
         for (int j = 0; j < kDwPXW; ++j) {
             if (px_ok[j]) {
                 const float ox = silu_f(acc[j].x + bias.x), oy = silu_f(acc[j].y + bias.y);
                 lsum.x += ox; lsum.y += oy;
-                *reinterpret_cast<uint32_t*>(row + j * p.C) = pack_half2(ox, oy);
+                *reinterpret_cast<uint32_t*>(o_ptr + j * pxC) = pack_half2(ox, oy);
             }
         }
+        o_ptr += out_pitch;
     };
 
+    uint32_t cons_off = 0;            // byte offset of the stage being consumed
+    const uint32_t lds_base = ring_u32 + (uint32_t)(px_base * kDwCS + 2 * lane) * 2u;
     for (int js = 0; js < NSTG; ++js) {
         cp_async_wait<Cfg::NST - 2>();
         __syncthreads();
-        if (js + Cfg::NST - 1 < NSTG) issue(js + Cfg::NST - 1);
+        if (js + Cfg::NST - 1 < NSTG) issue();
         cp_async_commit();
 #pragma unroll
         for (int rr = 0; rr < Cfg::RPS; ++rr) {
             const int k = js * Cfg::RPS + rr;
             if (k >= NR) break;
-            const __half* st = s_ring + (js % Cfg::NST) * Cfg::STAGE_HALVES + rr * Cfg::STEP_HALVES + px_base * kDwCS + 2 * lane;
+            const uint32_t st = lds_base + cons_off + rr * (Cfg::STEP_HALVES * 2);
             const int yi = yi0 + k;
 
             if constexpr (STRIDE == 1) {
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
                     float2 v[Cfg::NV];
 #pragma unroll
                     for (int i = 0; i < Cfg::NV; ++i)
-                        v[i] = __half22float2(*reinterpret_cast<const __half2*>(st + dt * Cfg::ROW_HALVES + i * kDwCS));
+                        v[i] = lds_half2(st + (dt * Cfg::ROW_HALVES + i * kDwCS) * 2);
 #pragma unroll
                     for (int j = 0; j < kDwPXW; ++j)
 #pragma unroll
@@ -178,14 +192,14 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
                             a0[j] = ffma2(w[dt * 9 + 6 + s], v[j + s], a0[j]);
                         }
                 }
-                if (yi - 1 >= yo0) emit(yi - 1, a0);        // yi - 1 < yo1 always holds (yi <= yo1)
+                if (yi - 1 >= yo0) emit(a0);        // row yi - 1 (< yo1 always holds since yi <= yo1)
 #pragma unroll
                 for (int j = 0; j < kDwPXW; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; }
             } else {
                 // stride 2: even input row 2yo is kernel row 0 of out yo and kernel row 2 of out yo-1; odd row 2yo+1 is row 1
                 float2 v[Cfg::NV];
 #pragma unroll
-                for (int i = 0; i < Cfg::NV; ++i) v[i] = __half22float2(*reinterpret_cast<const __half2*>(st + i * kDwCS));
+                for (int i = 0; i < Cfg::NV; ++i) v[i] = lds_half2(st + i * kDwCS * 2);
                 if ((k & 1) == 0) {       // yi = 2*yo0 + k is even
 #pragma unroll
                     for (int j = 0; j < kDwPXW; ++j) {
@@ -196,7 +210,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
                             a2[j] = ffma2(w[0 + s], v[2 * j + s], a2[j]);     // opens out row yi/2
                         }
                     }
-                    if (k > 0) emit((yi >> 1) - 1, a1);
+                    if (k > 0) emit(a1);           // row yi/2 - 1
 #pragma unroll
                     for (int j = 0; j < kDwPXW; ++j) a1[j] = a2[j];
                 } else {
@@ -207,6 +221,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
                 }
             }
         }
+        cons_off += Cfg::STAGE_HALVES * 2;
+        if (cons_off == Cfg::NST * Cfg::STAGE_HALVES * 2) cons_off = 0;
     }
     cp_async_wait<0>();
 
