@@ -87,7 +87,7 @@ class MultiDimStacker(nn.Module):
                  index_2d_features: int = 4, pretrained: bool = False, num_3d_blocks: int = 2,
                  num_3d_features: int = 192, num_3d_stack_proj: int = 256, expansion_3d_ratio: int = 6,
                  se_reduce_3d_ratio: int = 24, drop_rate: float = 0., drop_path_rate: float = 0.,
-                 act_layer: str = "silu", chunk_images: int = 0, **kwargs):
+                 act_layer: str = "silu", chunk_images: int = 0, bias_correction: bool = True, **kwargs):
         super().__init__()
         assert num_frames > 0 and num_frames % stack_size == 0            # multidim_stacker.py:155
         if model_name.split(".")[0] != "tf_efficientnetv2_b0":
@@ -112,6 +112,7 @@ class MultiDimStacker(nn.Module):
         self.conv3d_projection = nn.Sequential(_conv2d(num_3d_features, num_3d_stack_proj, 1), _bn2d(num_3d_stack_proj, 1e-5))
         self.global_pool = _GeMParams(3.0)
         self.classifier = nn.Linear(self.num_features, num_classes, bias=True)
+        self._bias_correction = bias_correction      # packer.py: data-free correction of the fp16 weight-rounding bias
         self._engine: Optional[Engine] = None
         self._dirty = True
 
@@ -164,10 +165,10 @@ class MultiDimStacker(nn.Module):
             self._engine.close()
             self._engine = None
         if self._engine is None:
-            self._engine = Engine(self._cfg, pack_state_dict(self.state_dict(), self._cfg.num_3d_blocks), dev)
+            self._engine = Engine(self._cfg, pack_state_dict(self.state_dict(), self._cfg.num_3d_blocks, self._bias_correction), dev)
             self._dirty = False
         elif self._dirty:
-            self._engine.load_packed(pack_state_dict(self.state_dict(), self._cfg.num_3d_blocks))
+            self._engine.load_packed(pack_state_dict(self.state_dict(), self._cfg.num_3d_blocks, self._bias_correction))
             self._dirty = False
         return self._engine
 

@@ -56,20 +56,56 @@ def bias_matrix(b: torch.Tensor) -> torch.Tensor:
     return m.contiguous()
 
 
-def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str, torch.Tensor]:
+_GH = None
+
+
+def _silu_mean(beta: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    """E[SiLU(z)], z ~ N(beta, gamma^2) per channel (48-point Gauss-Hermite): the mean of a BN+SiLU output whose
+    running statistics match its input, i.e. of any trained BatchNorm layer."""
+    global _GH
+    if _GH is None:
+        import numpy as np
+        x, w = np.polynomial.hermite_e.hermegauss(48)
+        _GH = (torch.tensor(x, dtype=torch.float64), torch.tensor(w / w.sum(), dtype=torch.float64))
+    z = beta.double()[:, None] + gamma.double().abs()[:, None] * _GH[0][None, :]
+    return (torch.nn.functional.silu(z) * _GH[1][None, :]).sum(1)
+
+
+def _rounding_bias(w: torch.Tensor, mu) -> torch.Tensor:
+    """Expected output shift caused by rounding the folded weights to fp16: sum_k (fp16(w) - w)[n, k] * E[x_k].
+    With few, mostly positive (post-SiLU) input channels this shift is the same at every pixel, so it survives the
+    GeM average; subtracting it from the bias is the data-free "bias correction" of post-training quantisation
+    (Nagel et al., DFQ, ICCV 2019), with E[x] taken from the preceding BatchNorm's (beta, gamma)."""
+    if mu is None:
+        return torch.zeros(w.shape[0], dtype=torch.float64)
+    dw = w.to(torch.float16).double() - w
+    return (dw.reshape(w.shape[0], w.shape[1], -1).sum(-1) * mu[None, :]).sum(1)
+
+
+def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int, bias_correction: bool = True) -> Dict[str, torch.Tensor]:
     out: Dict[str, torch.Tensor] = {}
     e = "conv2d_encoder."
     w, b = _fold(sd, e + "conv_stem.weight", e + "bn1", ENC_EPS)           # [32][3][3][3]
     out["stem.wh"] = stem_weights(w)
     out["stem.b"] = _f(b)
 
-    def conv3(name, wkey, bn):
+    def beta(bn):
+        return sd[bn + ".bias"].detach().double().cpu()
+
+    def act_mean(bn):
+        return _silu_mean(sd[bn + ".bias"].detach().cpu(), sd[bn + ".weight"].detach().cpu())
+
+    def conv3(name, wkey, bn, mu=None):
         w, b = _fold(sd, wkey, bn, ENC_EPS)                                # [co][ci][3][3]
+        if bias_correction:
+            b = b - _rounding_bias(w, mu)
         out[name + ".w"] = _h(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))   # [co][(r*3+s)*ci + c]
         out[name + ".b"] = _f(b)
 
-    def pw(name, wkey, bn, eps, bias_mat=False, gated=False):
+    def pw(name, wkey, bn, eps, bias_mat=False, gated=False, mu=None):
         w, b = _fold(sd, wkey, bn, eps)
+        if bias_correction and not gated:      # gated weights are rounded per image at run time: nothing static to correct
+            b = b - _rounding_bias(w, mu)
         out[name + ".w"] = _h(w.reshape(w.shape[0], w.shape[1]))            # [co][ci]
         out[name + ".b"] = _f(b)
         if bias_mat or gated:
@@ -89,28 +125,38 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], num_3d_blocks: int) -> Dict[str
         out[name + ".w2t"] = _f(w2.detach().cpu().reshape(w2.shape[0], w2.shape[1]).t())      # [rd][C]
         out[name + ".b2"] = _f(sd[prefix + ".conv_expand.bias"].detach().cpu())
 
-    for si, (kind, reps, _, _, _, _) in enumerate(STAGES):
+    # mu = expected per-channel mean of the tensor that flows between blocks (used only for the bias correction)
+    mu = act_mean(e + "bn1")
+    cin = 32
+    for si, (kind, reps, stride, _, cout, _) in enumerate(STAGES):
         for bi in range(reps):
             p, n = f"{e}blocks.{si}.{bi}.", f"b{si}.{bi}"
+            skip = kind != "cn" and (stride if bi == 0 else 1) == 1 and cin == cout
             if kind == "cn":
-                conv3(n + ".c3", p + "conv.weight", p + "bn1")
+                conv3(n + ".c3", p + "conv.weight", p + "bn1", mu)
+                mu = act_mean(p + "bn1")
             elif kind == "er":
-                conv3(n + ".c3", p + "conv_exp.weight", p + "bn1")
-                pw(n + ".pwl", p + "conv_pwl.weight", p + "bn2", ENC_EPS)
+                conv3(n + ".c3", p + "conv_exp.weight", p + "bn1", mu)
+                pw(n + ".pwl", p + "conv_pwl.weight", p + "bn2", ENC_EPS, mu=act_mean(p + "bn1"))
+                mu = beta(p + "bn2") + (mu if skip else 0)
             else:
-                pw(n + ".pw", p + "conv_pw.weight", p + "bn1", ENC_EPS, bias_mat=True)
+                pw(n + ".pw", p + "conv_pw.weight", p + "bn1", ENC_EPS, bias_mat=True, mu=mu)
                 dw(n + ".dw", p + "conv_dw.weight", p + "bn2", ENC_EPS)
                 se(n + ".se", p + "se")
                 pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3", ENC_EPS, gated=True)
+                mu = beta(p + "bn3") + (mu if skip else 0)
+            cin = cout
 
-    pw("proj2d", "conv2d_projection.0.weight", "conv2d_projection.1", REF_EPS, bias_mat=True)
+    pw("proj2d", "conv2d_projection.0.weight", "conv2d_projection.1", REF_EPS, bias_mat=True, mu=mu)
+    mu = act_mean("conv2d_projection.1")
     for i in range(num_3d_blocks):
         p, n = f"conv3d_encoder.{i}.", f"c3d.{i}"
-        pw(n + ".pw", p + "conv_pw.weight", p + "bn1.bn3d", REF_EPS, bias_mat=True)
+        pw(n + ".pw", p + "conv_pw.weight", p + "bn1.bn3d", REF_EPS, bias_mat=True, mu=mu)
         dw(n + ".dw", p + "conv_dw.weight", p + "bn2.bn3d", REF_EPS)
         se(n + ".se", p + "se")
         pw(n + ".pwl", p + "conv_pwl.weight", p + "bn3.bn3d", REF_EPS, gated=True)
-    pw("proj3d", "conv3d_projection.0.weight", "conv3d_projection.1", REF_EPS, bias_mat=True)
+        mu = beta(p + "bn3.bn3d") + mu            # the 3D shortcut is unconditional (multidim_stacker.py:133)
+    pw("proj3d", "conv3d_projection.0.weight", "conv3d_projection.1", REF_EPS, bias_mat=True, mu=mu)
     out["gem.p"] = _f(sd["global_pool.p"].detach().cpu().reshape(1))
     out["cls.w"] = _f(sd["classifier.weight"].detach().cpu())
     out["cls.b"] = _f(sd["classifier.bias"].detach().cpu())

@@ -54,7 +54,7 @@ def test_no_cpu_fallback(oracle_sd):
 
 def test_bn_folding_reproduces_conv_bn(oracle_sd):
     from ball_action_spotting_b200.packer import pack_state_dict
-    pk = pack_state_dict(oracle_sd, 4)
+    pk = pack_state_dict(oracle_sd, 4, bias_correction=False)
     g = torch.Generator().manual_seed(0)
     # dense 3x3 (blocks.1.1.conv_exp + bn1): packed [co][(r*3+s)*ci + c] fp16 / bias fp32
     x = torch.randn(1, 32, 12, 12, generator=g)
@@ -90,3 +90,17 @@ def test_host_mirrors_equal_oracle_restatements():
     u8 = torch.randint(0, 256, (2, 3, 720, 1280), dtype=torch.uint8, generator=torch.Generator().manual_seed(1))
     proc = get_frames_processor("pad_normalize", dict(size=(1280, 736), pad_mode="constant", fill_value=0))
     assert torch.equal(proc(u8), O.pad_normalize(u8, (1280, 736)))
+
+
+def test_bias_correction_is_tiny_and_data_free(oracle_sd):
+    """The fp16 rounding-bias correction only nudges biases (<< one fp16 ulp of the activations) and touches nothing else."""
+    from ball_action_spotting_b200.packer import pack_state_dict
+    a = pack_state_dict(oracle_sd, 4, bias_correction=False)
+    b = pack_state_dict(oracle_sd, 4, bias_correction=True)
+    assert a.keys() == b.keys()
+    changed = [k for k in a if not torch.equal(a[k], b[k])]
+    assert changed and all(k.endswith(".b") or k.endswith(".bm") for k in changed)
+    for k in changed:
+        if k.endswith(".b"):
+            assert (a[k] - b[k]).abs().max() < 5e-3
+    assert not any(".pwl" in k and k.startswith(("b3", "b4", "b5", "c3d")) for k in changed)     # SE-gated layers are untouched
