@@ -40,8 +40,8 @@ SIGNATURES = {
     "mds_k_stem": (_i, [_FP, _i, _vp, _vp, _vp, _vp]),
     "mds_k_conv3x3": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mds_k_gemm1x1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "mds_k_dwconv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "mds_k_se_fc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "mds_k_dwconv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mds_k_se_fc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "mds_k_gemm_gated": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mds_k_gem": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp]),
     "mds_k_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

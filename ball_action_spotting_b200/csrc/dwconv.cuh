@@ -1,5 +1,5 @@
 // K4/K6: depthwise 3x3 (2D, stride 1/2, TF-SAME) and 3x3x3 (3D, pad 1) convolution + folded BN + SiLU, NHWC fp16,
-// with the SE squeeze (per-image channel sums over the output, fp32) produced in the same pass
+// with the SE squeeze (per-image channel sums over the output, fp32, as per-CTA partials) produced in the same pass
 // (timm InvertedResidual conv_dw/bn2/se; multidim_stacker.py:110-114,86).
 //
 // HBM-bound streaming kernel.  A CTA owns (image, [out plane t], 40 output columns, 64-channel slab, row chunk) and
@@ -19,9 +19,9 @@ struct DwParams {
     __half* out;         // [n][T][Ho][Wo][C]
     const float* w;      // [taps][C]  tap = (dt*3 + r)*3 + s, BN scale folded
     const float* bias;   // [C]
-    float* sums;         // [n][C]  += sum over (T,Ho,Wo) of the fp32 SiLU output
+    float* partials;     // [n][nparts][C]  per-CTA sums over its part of (T,Ho,Wo) of the fp32 SiLU output (deterministic SE squeeze)
     int n, T, H, W, C, Ho, Wo;
-    int rows_per_chunk, chunks, xtiles, slabs;
+    int rows_per_chunk, chunks, xtiles, slabs, nparts;
 };
 
 constexpr int kDwCS = 64;      // channels per slab (lane = 2 channels)
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     }
     cp_async_wait<0>();
 
-    // ---- SE squeeze: reduce the 8 warps' partial sums, one global atomic per channel per CTA ----
+    // ---- SE squeeze: reduce the 8 warps' partial sums in a fixed order; one plain store per channel per CTA ----
     s_part[warp * kDwCS + 2 * lane] = lsum.x;
     s_part[warp * kDwCS + 2 * lane + 1] = lsum.y;
     __syncthreads();
@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += s_part[i * kDwCS + tid];
-        atomicAdd(p.sums + (size_t)n * p.C + c_slab + tid, s);
+        const int part = blockIdx.y * p.xtiles + xt;       // (t, row chunk, column tile)
+        p.partials[((size_t)n * p.nparts + part) * p.C + c_slab + tid] = s;
     }
 }
 

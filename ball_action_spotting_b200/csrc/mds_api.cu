@@ -343,8 +343,9 @@ static int launch_dw_t(const DwParams& p, dim3 grid, cudaStream_t st) {
     return MDS_OK;
 }
 
-static int launch_dw(const __half* in, __half* out, const float* w, const float* bias, float* sums, int n, int T,
-                     int H, int W, int C, int kt, int stride, cudaStream_t st) {
+constexpr int kDwMaxParts = 64;     // upper bound on the squeeze partials per image (workspace sizing)
+static int launch_dw(const __half* in, __half* out, const float* w, const float* bias, float* partials, int* nparts_out, int n,
+                     int T, int H, int W, int C, int kt, int stride, cudaStream_t st) {
     if (C % 8 || C > 4096) return fail(MDS_ERR_INVALID, "dwconv: C must be a multiple of 8");
     if (!((kt == 1 && (stride == 1 || stride == 2)) || (kt == 3 && stride == 1)))
         return fail(MDS_ERR_INVALID, "dwconv: unsupported kt=%d stride=%d", kt, stride);
@@ -353,7 +354,7 @@ static int launch_dw(const __half* in, __half* out, const float* w, const float*
     if (n <= 0) return MDS_OK;
     if (n > 65535) return fail(MDS_ERR_INVALID, "dwconv: n too large");
     DwParams p;
-    p.in = in; p.out = out; p.w = w; p.bias = bias; p.sums = sums;
+    p.in = in; p.out = out; p.w = w; p.bias = bias; p.partials = partials;
     p.n = n; p.T = T; p.H = H; p.W = W; p.C = C;
     p.Ho = H / stride; p.Wo = W / stride;
     p.xtiles = (p.Wo + kDwTWX - 1) / kDwTWX;
@@ -367,22 +368,25 @@ static int launch_dw(const __half* in, __half* out, const float* w, const float*
         const int max_chunks = p.Ho / 6 > 0 ? p.Ho / 6 : 1;
         if (chunks > max_chunks) chunks = max_chunks;
     }
+    while (chunks > 1 && (long long)chunks * T * p.xtiles > kDwMaxParts) --chunks;
     p.rows_per_chunk = (p.Ho + chunks - 1) / chunks;
     p.chunks = (p.Ho + p.rows_per_chunk - 1) / p.rows_per_chunk;
-    if ((long long)p.chunks * T > 65535) return fail(MDS_ERR_INVALID, "dwconv: grid.y too large");
+    p.nparts = p.chunks * T * p.xtiles;
+    if (p.nparts > kDwMaxParts) return fail(MDS_ERR_INVALID, "dwconv: %d squeeze partials per image exceed %d (T=%d, W=%d)", p.nparts, kDwMaxParts, T, W);
+    if (nparts_out) *nparts_out = p.nparts;
     dim3 grid(p.xtiles * p.slabs, p.chunks * T, n);
     if (kt == 3) return launch_dw_t<3, 1>(p, grid, st);
     if (stride == 1) return launch_dw_t<1, 1>(p, grid, st);
     return launch_dw_t<1, 2>(p, grid, st);
 }
 
-static int launch_se(const float* sums, float* sums_next, const float* w1, const float* b1, const float* w2t, const float* b2,
+static int launch_se(const float* partials, int nparts, const float* w1, const float* b1, const float* w2t, const float* b2,
                      __half* gate, const float* w32, __half* wg, int n, int C, int rd, int N, float inv_count, cudaStream_t st) {
     if (n <= 0) return MDS_OK;
     if (C > 4096 || rd > 256 || C % 8) return fail(MDS_ERR_INVALID, "se_fc: C must be a multiple of 8, C <= 4096, rd <= 256");
-    if (n > 65535) return fail(MDS_ERR_INVALID, "se_fc: n too large");
+    if (n > 65535 || nparts <= 0) return fail(MDS_ERR_INVALID, "se_fc: bad n / nparts");
     SeParams p;
-    p.sums = sums; p.sums_next = sums_next; p.w1 = w1; p.b1 = b1; p.w2t = w2t; p.b2 = b2; p.gate = gate;
+    p.partials = partials; p.nparts = nparts; p.w1 = w1; p.b1 = b1; p.w2t = w2t; p.b2 = b2; p.gate = gate;
     p.w32 = w32; p.wg = (w32 != nullptr) ? wg : nullptr; p.C = C; p.rd = rd; p.N = N; p.inv_count = inv_count;
     const int gps = ((C >> 3) + kSeSlices - 1) / kSeSlices;
     const size_t smem = (size_t)(C + ((rd + 3) & ~3) + gps * 8) * sizeof(float);
@@ -649,12 +653,12 @@ static size_t ws2d_bytes(const MdsHandle* h, int H, int W, int n_images) {
     if (cs <= 0) cs = 1;
     Sizes2d s = sizes2d(H, W);
     return 2 * al256(s.stream_elems * cs * 2) + al256(s.mid1_elems * cs * 2) + al256(s.mid2_elems * cs * 2) +
-           2 * al256((size_t)cs * 1152 * 4) + al256((size_t)cs * 1152 * 2) + al256((size_t)cs * kMaxGatedW * 2);
+           al256((size_t)cs * kDwMaxParts * 1152 * 4) + al256((size_t)cs * 1152 * 2) + al256((size_t)cs * kMaxGatedW * 2);
 }
 static size_t ws3d_bytes(const MdsHandle* h, int b, int P) {
     const size_t rows = (size_t)b * h->T() * P;
     return 2 * al256(rows * h->cfg.num_3d_features * 2) + 2 * al256(rows * h->mid3d() * 2) +
-           2 * al256((size_t)b * h->mid3d() * 4) + al256((size_t)b * h->mid3d() * 2) +
+           al256((size_t)b * kDwMaxParts * h->mid3d() * 4) + al256((size_t)b * h->mid3d() * 2) +
            al256((size_t)b * h->cfg.num_3d_features * h->mid3d() * 2);
 }
 static size_t wshead_bytes(const MdsHandle* h, int b) { return al256((size_t)b * h->cfg.num_3d_stack_proj * h->T() * 4); }
@@ -690,16 +694,11 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
     X[1] = ar.take<__half>(sz.stream_elems * cs_max);
     __half* M1 = ar.take<__half>(sz.mid1_elems * cs_max);
     __half* M2 = ar.take<__half>(sz.mid2_elems * cs_max);
-    float* sums2[2];
-    sums2[0] = ar.take<float>((size_t)cs_max * 1152);
-    sums2[1] = ar.take<float>((size_t)cs_max * 1152);
+    float* partials = ar.take<float>((size_t)cs_max * kDwMaxParts * 1152);
     __half* gate = ar.take<__half>((size_t)cs_max * 1152);
     __half* wg = ar.take<__half>((size_t)cs_max * kMaxGatedW);
     if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_2d: workspace too small");
-    // SE squeeze sums ping-pong between two buffers: layer i accumulates into sums2[i & 1] (pre-cleared by the SE kernel
-    // of layer i-1).  Both start cleared.  Buffers are laid out [image][C of that layer].
-    CUDA_TRY(cudaMemsetAsync(sums2[0], 0, 2 * al256((size_t)cs_max * 1152 * sizeof(float)), st));
-    int se_layer = 0;
+
     const int elem = fr.dtype == 0 ? 1 : 4;
     const int P = (fr.H / 32) * (fr.W / 32);
 
@@ -719,11 +718,9 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
                 TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, b.w2, b.b2, cs, hh, ww, b.cin, b.mid, b.stride, b.cout, b.skip, st));
             } else {
                 TRY(launch_gemm(X[cur], b.wpw, b.bpw, nullptr, nullptr, M1, (long long)hh * ww, cs, b.mid, b.cin, 1, st, b.bmpw));
-                float* sums = sums2[se_layer & 1];
-                float* sums_next = sums2[(se_layer + 1) & 1];
-                ++se_layer;
-                TRY(launch_dw(M1, M2, b.wdw, b.bdw, sums, cs, 1, hh, ww, b.mid, 1, b.stride, st));
-                TRY(launch_se(sums, sums_next, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, b.w32pwl, wg, cs, b.mid, b.rd, b.cout,
+                int nparts = 0;
+                TRY(launch_dw(M1, M2, b.wdw, b.bdw, partials, &nparts, cs, 1, hh, ww, b.mid, 1, b.stride, st));
+                TRY(launch_se(partials, nparts, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, b.w32pwl, wg, cs, b.mid, b.rd, b.cout,
                               1.0f / (float)(ho * wo), st));
                 TRY(launch_gemm_tc_stream(M2, wg, b.bmpwl, b.skip ? X[cur] : nullptr, X[cur ^ 1], ho * wo, cs, b.cout, b.mid, 0, st));
             }
@@ -747,14 +744,11 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
     Y[1] = ar.take<__half>(rows * c3);
     __half* M1 = ar.take<__half>(rows * mid);
     __half* M2 = ar.take<__half>(rows * mid);
-    float* sums2[2];
-    sums2[0] = ar.take<float>((size_t)b * mid);
-    sums2[1] = ar.take<float>((size_t)b * mid);
+    float* partials = ar.take<float>((size_t)b * kDwMaxParts * mid);
     __half* gate = ar.take<__half>((size_t)b * mid);
     __half* wg = ar.take<__half>((size_t)b * c3 * mid);
     if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_3d: workspace too small");
-    CUDA_TRY(cudaMemsetAsync(sums2[0], 0, 2 * al256((size_t)b * mid * sizeof(float)), st));
-    int se_layer = 0;
+
     const __half* x = feats;
     int nxt = 0;
     // the 2D features are [b][T][h][w][C] already, i.e. the reference's transpose(1,2) is a no-op in NDHWC
@@ -763,11 +757,9 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
     for (const Block3d& blk : h->blocks3d) {
         ++g_prof_tag;
         TRY(launch_gemm(x, blk.wpw, blk.bpw, nullptr, nullptr, M1, (long long)T * P, b, mid, c3, 1, st, blk.bmpw));
-        float* sums = sums2[se_layer & 1];
-        float* sums_next = sums2[(se_layer + 1) & 1];
-        ++se_layer;
-        TRY(launch_dw(M1, M2, blk.wdw, blk.bdw, sums, b, T, fh, fw, mid, 3, 1, st));
-        TRY(launch_se(sums, sums_next, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, blk.w32pwl, wg, b, mid, rd, c3,
+        int nparts = 0;
+        TRY(launch_dw(M1, M2, blk.wdw, blk.bdw, partials, &nparts, b, T, fh, fw, mid, 3, 1, st));
+        TRY(launch_se(partials, nparts, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, blk.w32pwl, wg, b, mid, rd, c3,
                       1.0f / (float)((size_t)T * P), st));
         TRY(launch_gemm_tc_stream(M2, wg, blk.bmpwl, x, Y[nxt], T * P, b, c3, mid, 0, st));
         x = Y[nxt];
@@ -878,14 +870,14 @@ extern "C" int mds_k_gemm1x1(const void* A, const void* W, const float* bias, co
                        reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream),
                        reinterpret_cast<const __half*>(bias_mat));
 }
-extern "C" int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* sums, int n, int T, int H,
-                            int W, int C, int kt, int stride, void* stream) {
-    return launch_dw(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), w, bias, sums, n, T, H, W, C, kt,
-                     stride, reinterpret_cast<cudaStream_t>(stream));
+extern "C" int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* partials, int* nparts, int n,
+                            int T, int H, int W, int C, int kt, int stride, void* stream) {
+    return launch_dw(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), w, bias, partials, nparts, n, T, H, W, C,
+                     kt, stride, reinterpret_cast<cudaStream_t>(stream));
 }
-extern "C" int mds_k_se_fc(const float* sums, float* sums_next, const float* w1, const float* b1, const float* w2t, const float* b2,
+extern "C" int mds_k_se_fc(const float* partials, int nparts, const float* w1, const float* b1, const float* w2t, const float* b2,
                            void* gate, const float* w32, void* wg, int n, int C, int rd, int N, float inv_count, void* stream) {
-    return launch_se(sums, sums_next, w1, b1, w2t, b2, reinterpret_cast<__half*>(gate), w32, reinterpret_cast<__half*>(wg), n, C,
+    return launch_se(partials, nparts, w1, b1, w2t, b2, reinterpret_cast<__half*>(gate), w32, reinterpret_cast<__half*>(wg), n, C,
                      rd, N, inv_count, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int mds_k_gemm_gated(const void* A, const void* wg, const void* bias_mat, const void* res, void* C, int rows_per_img,

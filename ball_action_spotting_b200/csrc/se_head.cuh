@@ -8,11 +8,12 @@ namespace mds {
 // grid = (images, kSeSlices): every CTA recomputes the tiny squeeze FC, then owns one slice of the channels: it writes
 // their gates and — when wg != nullptr — the slice's columns of this image's gated projection weights
 //     wg[n][o][c] = fp16( w32[o][c] * gate[c] )          (fp32 product, ONE rounding)
-// which the tcgen05 projection GEMM consumes through a 3-D tensor map.  Slice 0 also clears `sums_next` (the buffer the
-// next depthwise layer accumulates into; sums ping-pong between two buffers so no CTA clears what another still reads).
+// which the tcgen05 projection GEMM consumes through a 3-D tensor map.  The squeeze is deterministic: the depthwise
+// kernel leaves one partial sum per CTA and they are added here in a fixed order (no float atomics anywhere on the
+// path, so the whole forward is bit-reproducible).
 struct SeParams {
-    const float* sums;    // [n][C]
-    float* sums_next;     // [n][C] or nullptr
+    const float* partials;   // [n][nparts][C]
+    int nparts;
     const float* w1;      // [rd][C]
     const float* b1;      // [rd]
     const float* w2t;     // [rd][C]  (conv_expand weight transposed)
@@ -32,10 +33,17 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
     float* s_hid = s_se + p.C;       // [rd]
     float* s_gate = s_hid + ((p.rd + 3) & ~3);   // [slice width]
     const int n = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* sums = p.sums + (size_t)n * p.C;
-    for (int c = tid; c < p.C; c += kSeThreads) s_mean[c] = sums[c] * p.inv_count;
-    if (slice == 0 && p.sums_next != nullptr)
-        for (int c = tid; c < p.C; c += kSeThreads) p.sums_next[(size_t)n * p.C + c] = 0.f;
+    const float* part = p.partials + (size_t)n * p.nparts * p.C;
+    for (int c = tid; c < p.C; c += kSeThreads) {      // fixed summation order; 4 loads in flight per step
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int q = 0;
+        for (; q + 3 < p.nparts; q += 4) {
+            a0 += __ldg(part + (size_t)q * p.C + c);       a1 += __ldg(part + (size_t)(q + 1) * p.C + c);
+            a2 += __ldg(part + (size_t)(q + 2) * p.C + c); a3 += __ldg(part + (size_t)(q + 3) * p.C + c);
+        }
+        for (; q < p.nparts; ++q) a0 += __ldg(part + (size_t)q * p.C + c);
+        s_mean[c] = ((a0 + a1) + (a2 + a3)) * p.inv_count;
+    }
     __syncthreads();
     // squeeze FC: one hidden unit per warp pass, 4 independent partial sums per lane so the loads overlap
     for (int j = warp; j < p.rd; j += kSeThreads / 32) {

@@ -101,11 +101,13 @@ int mds_k_conv3x3(const void* in, void* out, const void* w1, const float* b1, co
  * ungated GEMMs with K <= 192 (the bias is then added by the tensor core). */
 int mds_k_gemm1x1(const void* A, const void* W, const float* bias, const void* bias_mat, const void* res, const void* gate,
                   void* C, int rows_per_img, int n_img, int N, int K, int act, void* stream);
-int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* sums,
+/* partials: f32 [n][*nparts][C] (room for 64 parts per image): per-CTA sums of the output for the SE squeeze, every
+ * element written (no atomics, nothing to clear); *nparts receives the number of parts this launch produced. */
+int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* partials, int* nparts,
                  int n, int T, int H, int W, int C, int kt, int stride, void* stream);
-/* SE excitation. sums_next (optional) is cleared for the next layer; w32 [N][C] fp32 + wg [n][N][C] fp16 (optional):
- * per-image gated projection weights wg = fp16(w32 * gate) for mds_k_gemm_gated. */
-int mds_k_se_fc(const float* sums, float* sums_next, const float* w1, const float* b1, const float* w2t, const float* b2,
+/* SE excitation from the depthwise kernel's partial sums (added in a fixed order: deterministic); w32 [N][C] fp32 +
+ * wg [n][N][C] fp16 (optional): per-image gated projection weights wg = fp16(w32 * gate) for mds_k_gemm_gated. */
+int mds_k_se_fc(const float* partials, int nparts, const float* w1, const float* b1, const float* w2t, const float* b2,
                 void* gate, const float* w32, void* wg, int n, int C, int rd, int N, float inv_count, void* stream);
 /* SE-gated projection GEMM on tcgen05: C[img] = act(A[img] . wg[img]^T + bias) (+ res); N <= 256. */
 int mds_k_gemm_gated(const void* A, const void* wg, const void* bias_mat, const void* res, void* C, int rows_per_img,

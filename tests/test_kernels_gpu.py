@@ -154,12 +154,18 @@ def test_dwconv2d_and_se_sums(lib, C_, stride):
     d_b = b.to(DEV)
     Ho, Wo = y.shape[-2:]
     out = torch.zeros((n, Ho, Wo, C_), dtype=torch.float16, device=DEV)
-    sums = torch.zeros((n, C_), dtype=torch.float32, device=DEV)
-    ok(lib.mds_k_dwconv(d_x.data_ptr(), out.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), sums.data_ptr(),
-                        n, 1, H, W, C_, 1, stride, None), lib)
-    torch.cuda.synchronize()
+    parts = torch.full((n, 64, C_), float("nan"), dtype=torch.float32, device=DEV)
+    nparts = C.c_int(0)
+    runs = []
+    for _ in range(2):
+        ok(lib.mds_k_dwconv(d_x.data_ptr(), out.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), parts.data_ptr(), C.byref(nparts),
+                            n, 1, H, W, C_, 1, stride, None), lib)
+        torch.cuda.synchronize()
+        runs.append(parts.view(-1)[: n * nparts.value * C_].clone())
     assert rel(nchw(out), y) <= TOL
+    sums = runs[0].view(n, nparts.value, C_).sum(1)
     assert rel(sums, y.sum((2, 3))) <= 1e-4          # fp32 squeeze sums of the un-rounded SiLU output
+    assert torch.equal(runs[0], runs[1])             # plain stores, no atomics: bit-identical
 
 
 @pytest.mark.parametrize("T", [5, 11])
@@ -173,11 +179,13 @@ def test_dwconv3d_and_se_sums(lib, T):
     d_w = w.reshape(C_, 27).t().contiguous().to(DEV)
     d_b = b.to(DEV)
     out = torch.zeros((n, T, H, W, C_), dtype=torch.float16, device=DEV)
-    sums = torch.zeros((n, C_), dtype=torch.float32, device=DEV)
-    ok(lib.mds_k_dwconv(d_x.data_ptr(), out.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), sums.data_ptr(),
+    parts = torch.full((n, 64, C_), float("nan"), dtype=torch.float32, device=DEV)
+    nparts = C.c_int(0)
+    ok(lib.mds_k_dwconv(d_x.data_ptr(), out.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), parts.data_ptr(), C.byref(nparts),
                         n, T, H, W, C_, 3, 1, None), lib)
     torch.cuda.synchronize()
     assert rel(out.permute(0, 4, 1, 2, 3), y) <= TOL
+    sums = parts.view(-1)[: n * nparts.value * C_].view(n, nparts.value, C_).sum(1)
     assert rel(sums, y.sum((2, 3, 4))) <= 1e-4
 
 
@@ -193,17 +201,25 @@ def test_se_fc_gate_and_gated_weights(lib, C_, rd, N):
     mean = sums / count
     ref = torch.sigmoid(F.silu(mean @ w1.t() + b1) @ w2.t() + b2)
     ref_wg = w32[None] * ref[:, None, :]                       # (n, N, C): what x*gate followed by conv_pwl multiplies by
-    d_s, d_w1, d_b1, d_w2t, d_b2, d_w32 = sums.to(DEV), w1.to(DEV), b1.to(DEV), w2.t().contiguous().to(DEV), b2.to(DEV), w32.to(DEV)
-    nxt = torch.ones((n, C_), dtype=torch.float32, device=DEV)
+    # the squeeze arrives as per-CTA partials [n][nparts][C]; split the sums into 3 unequal parts
+    parts = torch.stack([sums * 0.5, sums * 0.3, sums * 0.2], 1).contiguous()
+    mean = parts.sum(1) / count
+    ref = torch.sigmoid(F.silu(mean @ w1.t() + b1) @ w2.t() + b2)
+    ref_wg = w32[None] * ref[:, None, :]
+    d_s, d_w1, d_b1, d_w2t, d_b2, d_w32 = parts.to(DEV), w1.to(DEV), b1.to(DEV), w2.t().contiguous().to(DEV), b2.to(DEV), w32.to(DEV)
     gate = torch.zeros((n, C_), dtype=torch.float16, device=DEV)
     wg = torch.zeros((n, N, C_), dtype=torch.float16, device=DEV)
-    ok(lib.mds_k_se_fc(d_s.data_ptr(), nxt.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(), d_w2t.data_ptr(), d_b2.data_ptr(),
+    ok(lib.mds_k_se_fc(d_s.data_ptr(), 3, d_w1.data_ptr(), d_b1.data_ptr(), d_w2t.data_ptr(), d_b2.data_ptr(),
                        gate.data_ptr(), d_w32.data_ptr(), wg.data_ptr(), n, C_, rd, N, 1.0 / count, None), lib)
     torch.cuda.synchronize()
     assert rel(gate, ref) <= TOL
     assert rel(wg, ref_wg) <= TOL
-    assert float(nxt.abs().max()) == 0.0             # the next layer's squeeze buffer is handed over cleared
-    assert torch.equal(d_s.cpu(), sums)              # ... and the current one is left untouched
+    g1, w1_ = gate.clone(), wg.clone()
+    ok(lib.mds_k_se_fc(d_s.data_ptr(), 3, d_w1.data_ptr(), d_b1.data_ptr(), d_w2t.data_ptr(), d_b2.data_ptr(),
+                       gate.data_ptr(), d_w32.data_ptr(), wg.data_ptr(), n, C_, rd, N, 1.0 / count, None), lib)
+    torch.cuda.synchronize()
+    assert torch.equal(g1, gate) and torch.equal(w1_, wg)          # deterministic: no atomics
+    assert torch.equal(d_s.cpu(), parts)                           # inputs untouched
 
 
 GATED_CASES = [(96, 192, 0), (96, 384, 1), (112, 576, 0), (112, 672, 1), (192, 672, 0), (192, 1152, 1), (192, 576, 1)]
