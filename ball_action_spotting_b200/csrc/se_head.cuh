@@ -27,6 +27,7 @@ struct SeParams {
 
 constexpr int kSeThreads = 512;
 constexpr int kSeSlices = 8;
+constexpr int kSeUnits = 3;          // hidden units a warp accumulates concurrently (rd <= 48 -> one pass)
 __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
     extern __shared__ float s_se[];
     float* s_mean = s_se;            // [C]
@@ -45,50 +46,87 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
         s_mean[c] = ((a0 + a1) + (a2 + a3)) * p.inv_count;
     }
     __syncthreads();
-    // squeeze FC: one hidden unit per warp pass, 4 independent partial sums per lane so the loads overlap
-    for (int j = warp; j < p.rd; j += kSeThreads / 32) {
-        const float4* w = reinterpret_cast<const float4*>(p.w1 + (size_t)j * p.C);
+    // squeeze FC: each warp owns up to kSeUnits hidden units and walks the channels ONCE for all of them, so their
+    // weight loads are in flight together (the kernel is a chain of L2 latencies, not bandwidth)
+    {
+        constexpr int kWarps = kSeThreads / 32;
         const float4* m = reinterpret_cast<const float4*>(s_mean);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-        for (int c = lane; c < p.C / 4; c += 32) {
-            const float4 wv = __ldg(w + c), mv = m[c];
-            a0 = fmaf(wv.x, mv.x, a0); a1 = fmaf(wv.y, mv.y, a1); a2 = fmaf(wv.z, mv.z, a2); a3 = fmaf(wv.w, mv.w, a3);
+        const int c4n = p.C >> 2;
+        for (int j0 = warp; j0 < p.rd; j0 += kWarps * kSeUnits) {
+            float acc[kSeUnits];
+            const float4* wrow[kSeUnits];
+#pragma unroll
+            for (int u = 0; u < kSeUnits; ++u) {
+                acc[u] = 0.f;
+                const int j = j0 + u * kWarps;
+                wrow[u] = reinterpret_cast<const float4*>(p.w1 + (size_t)(j < p.rd ? j : j0) * p.C);
+            }
+#pragma unroll 3
+            for (int c = lane; c < c4n; c += 32) {
+                const float4 mv = m[c];
+#pragma unroll
+                for (int u = 0; u < kSeUnits; ++u) {
+                    const float4 wv = __ldg(wrow[u] + c);
+                    acc[u] = fmaf(wv.x, mv.x, fmaf(wv.y, mv.y, fmaf(wv.z, mv.z, fmaf(wv.w, mv.w, acc[u]))));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kSeUnits; ++u) {
+                const int j = j0 + u * kWarps;
+                const float a = warp_sum(acc[u]);
+                if (lane == 0 && j < p.rd) s_hid[j] = silu_f(a + __ldg(p.b1 + j));
+            }
         }
-        const float acc = warp_sum((a0 + a1) + (a2 + a3));
-        if (lane == 0) s_hid[j] = silu_f(acc + __ldg(p.b1 + j));
     }
     __syncthreads();
     // this CTA's channel slice, in units of 8 channels (16 bytes of fp16)
     const int groups = p.C >> 3, gps = (groups + kSeSlices - 1) / kSeSlices;
     const int c_lo = min(p.C, slice * gps * 8), c_hi = min(p.C, c_lo + gps * 8);
-    for (int c = c_lo + tid; c < c_hi; c += kSeThreads) {
-        float a0 = __ldg(p.b2 + c), a1 = 0.f;
-        int j = 0;
+    // expand FC + sigmoid: 4 lanes per channel split the hidden units, so each lane has rd/4 independent loads
+    for (int c0 = c_lo; c0 < c_hi; c0 += kSeThreads / 4) {
+        const int c = c0 + (tid >> 2), sub = tid & 3;
+        float a = 0.f;
+        if (c < c_hi) {
 #pragma unroll 4
-        for (; j + 1 < p.rd; j += 2) {
-            a0 = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], a0);
-            a1 = fmaf(__ldg(p.w2t + (size_t)(j + 1) * p.C + c), s_hid[j + 1], a1);
+            for (int j = sub; j < p.rd; j += 4) a = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], a);
         }
-        if (j < p.rd) a0 = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], a0);
-        const float gv = sigmoid_f(a0 + a1);
-        s_gate[c - c_lo] = gv;
-        p.gate[(size_t)n * p.C + c] = __float2half_rn(gv);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (c < c_hi && sub == 0) {
+            const float gv = sigmoid_f(a + __ldg(p.b2 + c));
+            s_gate[c - c_lo] = gv;
+            p.gate[(size_t)n * p.C + c] = __float2half_rn(gv);
+        }
     }
     if (p.wg == nullptr) return;
     __syncthreads();
     const int wgrp = (c_hi - c_lo) >> 3;                 // 8-channel groups in this slice
     __half* wg = p.wg + (size_t)n * p.N * p.C;
-    for (int i = tid; i < p.N * wgrp; i += kSeThreads) {
+    const int total = p.N * wgrp;
+    auto gate8 = [&](int i, const float4& x0, const float4& x1) {
         const int o = i / wgrp, gq = i - o * wgrp;
-        const int c = c_lo + gq * 8;
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.w32 + (size_t)o * p.C + c));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(p.w32 + (size_t)o * p.C + c + 4));
         const float* gp = s_gate + gq * 8;
         uint4 v;
         v.x = pack_half2(x0.x * gp[0], x0.y * gp[1]); v.y = pack_half2(x0.z * gp[2], x0.w * gp[3]);
         v.z = pack_half2(x1.x * gp[4], x1.y * gp[5]); v.w = pack_half2(x1.z * gp[6], x1.w * gp[7]);
-        *reinterpret_cast<uint4*>(wg + (size_t)o * p.C + c) = v;
+        *reinterpret_cast<uint4*>(wg + (size_t)o * p.C + c_lo + gq * 8) = v;
+    };
+    auto src = [&](int i) {
+        const int o = i / wgrp, gq = i - o * wgrp;
+        return reinterpret_cast<const float4*>(p.w32 + (size_t)o * p.C + c_lo + gq * 8);
+    };
+    int i = tid;
+    for (; i + kSeThreads < total; i += 2 * kSeThreads) {      // two items (four 16-byte loads) in flight per thread
+        const float4* s0 = src(i);
+        const float4* s1 = src(i + kSeThreads);
+        const float4 a0 = __ldg(s0), a1 = __ldg(s0 + 1), b0 = __ldg(s1), b1 = __ldg(s1 + 1);
+        gate8(i, a0, a1);
+        gate8(i + kSeThreads, b0, b1);
+    }
+    if (i < total) {
+        const float4* s0 = src(i);
+        const float4 a0 = __ldg(s0), a1 = __ldg(s0 + 1);
+        gate8(i, a0, a1);
     }
 }
 
