@@ -36,9 +36,13 @@ struct Conv3Cfg {
     static_assert(!RES || (STRIDE == 1 && CPROJ == CIN), "residual needs same shape");
 };
 
-template <int CIN, int CMID, int STRIDE, int CPROJ, bool RES, int MINB>
-__global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
+// MT = m16 pixel-row tiles per warp.  MT = 2: a warp owns two output rows, so every weight (B) fragment it loads from
+// shared memory feeds twice the MMAs (the kernel is bound by ldmatrix traffic, not by the tensor pipe); the CTA then
+// has 4 warps (128 threads) for the same 8x16 pixel tile.
+template <int CIN, int CMID, int STRIDE, int CPROJ, bool RES, int MINB, int MT>
+__global__ void __launch_bounds__(256 / MT, MINB) conv3x3_kernel(Conv3Params p) {
     using Cfg = Conv3Cfg<CIN, CMID, STRIDE, CPROJ, RES>;
+    constexpr int NT = 256 / MT;           // threads per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* s_w1 = reinterpret_cast<__half*>(smem_raw);
     __half* s_w2 = s_w1 + Cfg::W1_HALVES;
@@ -54,19 +58,19 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
     // ---- weights -> smem (once per CTA) ----
     {
         constexpr int CH1 = 9 * CIN / 8;   // 16 B chunks per W1 row
-        for (int i = tid; i < CMID * CH1; i += 256) {
+        for (int i = tid; i < CMID * CH1; i += NT) {
             int row = i / CH1, c = i - row * CH1;
             cp_async16(s_w1 + row * Cfg::W1P + c * 8, p.w1 + (size_t)row * 9 * CIN + c * 8, 16);
         }
         if constexpr (CPROJ > 0) {
             constexpr int CH2 = CMID / 8;
-            for (int i = tid; i < CPROJ * CH2; i += 256) {
+            for (int i = tid; i < CPROJ * CH2; i += NT) {
                 int row = i / CH2, c = i - row * CH2;
                 cp_async16(s_w2 + row * Cfg::W2P + c * 8, p.w2 + (size_t)row * CMID + c * 8, 16);
             }
-            for (int i = tid; i < CPROJ; i += 256) s_b2[i] = p.b2[i];
+            for (int i = tid; i < CPROJ; i += NT) s_b2[i] = p.b2[i];
         }
-        for (int i = tid; i < CMID; i += 256) s_b1[i] = p.b1[i];
+        for (int i = tid; i < CMID; i += NT) s_b1[i] = p.b1[i];
     }
 
     auto load_tile = [&](int t, __half* dst) {
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
         int gy0 = ty * Cfg::TH * STRIDE - Cfg::PAD, gx0 = tx * Cfg::TW * STRIDE - Cfg::PAD;
         const __half* base = p.in + (size_t)n * p.H * p.W * CIN;
         constexpr int CPP = CIN / 8;
-        for (int i = tid; i < Cfg::IH * Cfg::IW * CPP; i += 256) {
+        for (int i = tid; i < Cfg::IH * Cfg::IW * CPP; i += NT) {
             int pix = i / CPP, c8 = i - pix * CPP;
             int iy = pix / Cfg::IW, ix = pix - iy * Cfg::IW;
             int gy = gy0 + iy, gx = gx0 + ix;
@@ -107,9 +111,11 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
         cp_async_wait<1>();
         __syncthreads();
 
-        float acc[CMID / 8][4];
+        float acc[MT][CMID / 8][4];
 #pragma unroll
-        for (int j = 0; j < CMID / 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int j = 0; j < CMID / 8; ++j) { acc[mi][j][0] = acc[mi][j][1] = acc[mi][j][2] = acc[mi][j][3] = 0.f; }
 
         const uint32_t tile_addr = smem_u32(cur);
         const uint32_t w1_addr = smem_u32(s_w1);
@@ -123,34 +129,40 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
 #pragma unroll
             for (int rs = 0; rs < 9; ++rs) {
                 const int r = rs / 3, s = rs - r * 3;
-                const uint32_t a_base = tile_addr +
-                    2u * (uint32_t)(((warp * STRIDE + r) * Cfg::IW + a_pix * STRIDE + s) * Cfg::PIXP + a_kof);
 #pragma unroll
-                for (int kc = 0; kc < CIN / 16; ++kc) {
-                    uint32_t a[4];
-                    ldmatrix_x4(a, a_base + kc * 32);
-                    const int q = rs * (CIN / 16) + kc;
-                    mma16816(acc[0], a, breg[q][0], breg[q][1]);
-                    mma16816(acc[1], a, breg[q][2], breg[q][3]);
+                for (int mi = 0; mi < MT; ++mi) {
+                    const uint32_t a_base = tile_addr +
+                        2u * (uint32_t)((((warp * MT + mi) * STRIDE + r) * Cfg::IW + a_pix * STRIDE + s) * Cfg::PIXP + a_kof);
+#pragma unroll
+                    for (int kc = 0; kc < CIN / 16; ++kc) {
+                        uint32_t a[4];
+                        ldmatrix_x4(a, a_base + kc * 32);
+                        const int q = rs * (CIN / 16) + kc;
+                        mma16816(acc[mi][0], a, breg[q][0], breg[q][1]);
+                        mma16816(acc[mi][1], a, breg[q][2], breg[q][3]);
+                    }
                 }
             }
         } else {
 #pragma unroll 1
         for (int rs = 0; rs < 9; ++rs) {
             const int r = rs / 3, s = rs - r * 3;
-            const uint32_t a_base = tile_addr +
-                2u * (uint32_t)(((warp * STRIDE + r) * Cfg::IW + a_pix * STRIDE + s) * Cfg::PIXP + a_kof);
             const uint32_t b_base = w1_addr + 2u * (uint32_t)(b_nof * Cfg::W1P + rs * CIN + b_kof);
 #pragma unroll
             for (int kc = 0; kc < CIN / 16; ++kc) {
-                uint32_t a[4];
-                ldmatrix_x4(a, a_base + kc * 32);
+                uint32_t a[MT][4];
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi)
+                    ldmatrix_x4(a[mi], tile_addr + 2u * (uint32_t)((((warp * MT + mi) * STRIDE + r) * Cfg::IW + a_pix * STRIDE + s) * Cfg::PIXP + a_kof) + kc * 32);
 #pragma unroll
                 for (int nc = 0; nc < CMID / 16; ++nc) {
                     uint32_t b[4];
                     ldmatrix_x4(b, b_base + 2u * (uint32_t)(nc * 16 * Cfg::W1P) + kc * 32);
-                    mma16816(acc[2 * nc], a, b[0], b[1]);
-                    mma16816(acc[2 * nc + 1], a, b[2], b[3]);
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi) {
+                        mma16816(acc[mi][2 * nc], a[mi], b[0], b[1]);
+                        mma16816(acc[mi][2 * nc + 1], a[mi], b[2], b[3]);
+                    }
                 }
             }
         }
@@ -160,7 +172,9 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
         const int n = t / tiles_per_img;
         const int rem = t - n * tiles_per_img;
         const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-        const int oy = ty * Cfg::TH + warp;
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+        const int oy = ty * Cfg::TH + warp * MT + mi;
         const int ox_lo = tx * Cfg::TW + g, ox_hi = ox_lo + 8;
         const bool ok_lo = (oy < p.Ho) && (ox_lo < p.Wo), ok_hi = (oy < p.Ho) && (ox_hi < p.Wo);
         constexpr int COUT = CPROJ ? CPROJ : CMID;
@@ -172,8 +186,8 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
             for (int j = 0; j < CMID / 8; ++j) {
                 const int c = j * 8 + tq * 2;
                 const float bx = s_b1[c], by = s_b1[c + 1];
-                if (ok_lo) *reinterpret_cast<uint32_t*>(out_lo + c) = pack_half2(silu_f(acc[j][0] + bx), silu_f(acc[j][1] + by));
-                if (ok_hi) *reinterpret_cast<uint32_t*>(out_hi + c) = pack_half2(silu_f(acc[j][2] + bx), silu_f(acc[j][3] + by));
+                if (ok_lo) *reinterpret_cast<uint32_t*>(out_lo + c) = pack_half2(silu_f(acc[mi][j][0] + bx), silu_f(acc[mi][j][1] + by));
+                if (ok_hi) *reinterpret_cast<uint32_t*>(out_hi + c) = pack_half2(silu_f(acc[mi][j][2] + bx), silu_f(acc[mi][j][3] + by));
             }
         } else {
             float acc2[CPROJ / 8][4];
@@ -186,10 +200,10 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
                 {
                     const int c0 = kk * 16 + tq * 2, c1 = c0 + 8;
                     const float b00 = s_b1[c0], b01 = s_b1[c0 + 1], b10 = s_b1[c1], b11 = s_b1[c1 + 1];
-                    a[0] = pack_half2(silu_f(acc[2 * kk][0] + b00), silu_f(acc[2 * kk][1] + b01));
-                    a[1] = pack_half2(silu_f(acc[2 * kk][2] + b00), silu_f(acc[2 * kk][3] + b01));
-                    a[2] = pack_half2(silu_f(acc[2 * kk + 1][0] + b10), silu_f(acc[2 * kk + 1][1] + b11));
-                    a[3] = pack_half2(silu_f(acc[2 * kk + 1][2] + b10), silu_f(acc[2 * kk + 1][3] + b11));
+                    a[0] = pack_half2(silu_f(acc[mi][2 * kk][0] + b00), silu_f(acc[mi][2 * kk][1] + b01));
+                    a[1] = pack_half2(silu_f(acc[mi][2 * kk][2] + b00), silu_f(acc[mi][2 * kk][3] + b01));
+                    a[2] = pack_half2(silu_f(acc[mi][2 * kk + 1][0] + b10), silu_f(acc[mi][2 * kk + 1][1] + b11));
+                    a[3] = pack_half2(silu_f(acc[mi][2 * kk + 1][2] + b10), silu_f(acc[mi][2 * kk + 1][3] + b11));
                 }
 #pragma unroll
                 for (int nc = 0; nc < CPROJ / 16; ++nc) {
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
                 const float bx = s_b2[c], by = s_b2[c + 1];
                 float v0 = acc2[j][0] + bx, v1 = acc2[j][1] + by, v2 = acc2[j][2] + bx, v3 = acc2[j][3] + by;
                 if constexpr (RES) {   // shortcut = block input = centre tap of the halo tile
-                    const __half* rl = cur + ((warp + 1) * Cfg::IW + (g + 1)) * Cfg::PIXP + c;
+                    const __half* rl = cur + ((warp * MT + mi + 1) * Cfg::IW + (g + 1)) * Cfg::PIXP + c;
                     const __half* rh = rl + 8 * Cfg::PIXP;
                     float2 fl = __half22float2(*reinterpret_cast<const __half2*>(rl));
                     float2 fh = __half22float2(*reinterpret_cast<const __half2*>(rh));
@@ -215,6 +229,7 @@ __global__ void __launch_bounds__(256, MINB) conv3x3_kernel(Conv3Params p) {
                 if (ok_hi) *reinterpret_cast<uint32_t*>(out_hi + c) = pack_half2(v2, v3);
             }
         }
+        }   // mi
         __syncthreads();   // everyone is done with `cur` before the next-next prefetch overwrites it
     }
     cp_async_wait<0>();

@@ -132,10 +132,10 @@ static int launch_stem(const MdsFrames& f, int n, const __half* wh, const float*
     return MDS_OK;
 }
 
-template <int CIN, int CMID, int STRIDE, int CPROJ, bool RES, int MINB>
+template <int CIN, int CMID, int STRIDE, int CPROJ, bool RES, int MINB, int MT>
 static int launch_conv3_t(const Conv3Params& p, cudaStream_t st) {
     using Cfg = Conv3Cfg<CIN, CMID, STRIDE, CPROJ, RES>;
-    auto kern = conv3x3_kernel<CIN, CMID, STRIDE, CPROJ, RES, MINB>;
+    auto kern = conv3x3_kernel<CIN, CMID, STRIDE, CPROJ, RES, MINB, MT>;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -146,7 +146,7 @@ static int launch_conv3_t(const Conv3Params& p, cudaStream_t st) {
     int grid = num_sms() * MINB;
     if (grid > tiles) grid = tiles;
     ProfScope ps(MDS_KIND_CONV3X3, st);
-    kern<<<grid, 256, Cfg::SMEM, st>>>(p);
+    kern<<<grid, 256 / MT, Cfg::SMEM, st>>>(p);
     LAUNCH_CHECK("conv3x3");
     return MDS_OK;
 }
@@ -159,13 +159,13 @@ static int launch_conv3(const __half* in, __half* out, const __half* w1, const f
     p.n = n; p.H = H; p.W = W;
     p.Ho = (H + stride - 1) / stride; p.Wo = (W + stride - 1) / stride;
     if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv3x3: stride-2 input must be even");
-#define C3CASE(CI, CM, S, CP, R, MB) \
-    if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0)) return launch_conv3_t<CI, CM, S, CP, R, MB>(p, st);
-    C3CASE(32, 16, 1, 0, false, 2)      // blocks.0.0  ConvBnAct (weights in registers)
-    C3CASE(16, 64, 2, 32, false, 2)     // blocks.1.0  EdgeResidual s2
-    C3CASE(32, 128, 1, 32, true, 1)     // blocks.1.1
-    C3CASE(32, 128, 2, 48, false, 1)    // blocks.2.0
-    C3CASE(48, 192, 1, 48, true, 1)     // blocks.2.1
+#define C3CASE(CI, CM, S, CP, R, MB, MT) \
+    if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0)) return launch_conv3_t<CI, CM, S, CP, R, MB, MT>(p, st);
+    C3CASE(32, 16, 1, 0, false, 2, 1)      // blocks.0.0  ConvBnAct (weights in registers)
+    C3CASE(16, 64, 2, 32, false, 2, 2)     // blocks.1.0  EdgeResidual s2
+    C3CASE(32, 128, 1, 32, true, 2, 2)     // blocks.1.1 (111 KB smem, 255 regs x 128 threads: two CTAs per SM)
+    C3CASE(32, 128, 2, 48, false, 1, 1)    // blocks.2.0 (one 4-warp CTA per SM was slower here)
+    C3CASE(48, 192, 1, 48, true, 1, 1)     // blocks.2.1 (192 mid channels: two rows per warp would not fit the register file)
 #undef C3CASE
     return fail(MDS_ERR_INVALID, "conv3x3: unsupported shape cin=%d cmid=%d stride=%d cproj=%d res=%d", cin, cmid, stride, cproj, res);
 }
