@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "conv3x3.cuh"
+#include "conv3x3_tc.cuh"
 #include "dwconv.cuh"
 #include "gemm1x1.cuh"
 #include "gemm_tc.cuh"
@@ -114,6 +115,19 @@ static int num_sms() {
 // --------------------------------------------------------------------------------------------------------------
 // kernel launchers
 // --------------------------------------------------------------------------------------------------------------
+// ---- tcgen05 path: TMA tensor maps are encoded on the host through the driver entry point (no libcuda link) ----
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
 static int launch_stem(const MdsFrames& f, int n, const __half* wh, const float* bias, __half* out, cudaStream_t st) {
     if (f.H % 2 || f.W % 4 || f.H <= 0 || f.W <= 0) return fail(MDS_ERR_INVALID, "stem: H must be even, W a multiple of 4");
     if (f.img_stride % 4 || f.plane_stride % 4) return fail(MDS_ERR_INVALID, "stem: image / plane strides must be multiples of 4 elements");
@@ -151,6 +165,42 @@ static int launch_conv3_t(const Conv3Params& p, cudaStream_t st) {
     return MDS_OK;
 }
 
+// stride-1 FusedMBConv on tcgen05 (conv3x3_tc.cuh): halo tiles through a 5-D tensor map over NHWC seen as [n][C/8][H][W][8]
+template <int CIN, int CMID, int COUT>
+static int launch_conv3_tc(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2, const float* b2,
+                           int n, int H, int W, cudaStream_t st) {
+    using Cfg = Conv3TcCfg<CIN, CMID, COUT>;
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    CUtensorMap tm;
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(CIN / 8), (cuuint64_t)n};
+    cuuint64_t strides[4] = {(cuuint64_t)CIN * 2, (cuuint64_t)W * CIN * 2, 16, (cuuint64_t)H * W * CIN * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)Cfg::SW, (cuuint32_t)Cfg::SH, (cuuint32_t)(CIN / 8), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled(5d) failed (%d) n=%d H=%d W=%d C=%d", (int)r, n, H, W, CIN);
+    Conv3TcParams p;
+    p.in = in; p.out = out; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.n = n; p.H = H; p.W = W;
+    p.tiles_x = (W + Cfg::TW - 1) / Cfg::TW;
+    p.tiles_y = (H + Cfg::TH - 1) / Cfg::TH;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * n;
+    if (tiles <= 0) return MDS_OK;
+    auto kern = conv3x3_tc_kernel<CIN, CMID, COUT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    int grid = num_sms();
+    if (tiles < grid) grid = (int)tiles;
+    ProfScope ps(MDS_KIND_CONV3X3, st);
+    kern<<<grid, kTcThreads, Cfg::SMEM, st>>>(tm, p);
+    LAUNCH_CHECK("conv3x3_tc");
+    return MDS_OK;
+}
+
 static int launch_conv3(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2,
                         const float* b2, int n, int H, int W, int cin, int cmid, int stride, int cproj, int res,
                         cudaStream_t st) {
@@ -159,6 +209,9 @@ static int launch_conv3(const __half* in, __half* out, const __half* w1, const f
     p.n = n; p.H = H; p.W = W;
     p.Ho = (H + stride - 1) / stride; p.Wo = (W + stride - 1) / stride;
     if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv3x3: stride-2 input must be even");
+    static const bool use_tc = [] { const char* e = getenv("MDS_CONV_TC"); return !(e && e[0] == '0'); }();
+    if (use_tc && cin == 32 && cmid == 128 && stride == 1 && cproj == 32 && res == 1)
+        return launch_conv3_tc<32, 128, 32>(in, out, w1, b1, w2, b2, n, H, W, st);
 #define C3CASE(CI, CM, S, CP, R, MB, MT) \
     if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0)) return launch_conv3_t<CI, CM, S, CP, R, MB, MT>(p, st);
     C3CASE(32, 16, 1, 0, false, 2, 1)      // blocks.0.0  ConvBnAct (weights in registers)
@@ -186,19 +239,6 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
     kern<<<grid, 256, Cfg::SMEM, st>>>(p);
     LAUNCH_CHECK("gemm1x1");
     return MDS_OK;
-}
-
-// ---- tcgen05 path: TMA tensor maps are encoded on the host through the driver entry point (no libcuda link) ----
-static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-    }
-    return fn;
 }
 
 // fp16 row-major [rows][K] matrix, box = 64 (K) x box_rows, 128-byte swizzle, out-of-bounds elements read as zero
