@@ -209,8 +209,7 @@ static int launch_conv3(const __half* in, __half* out, const __half* w1, const f
     p.n = n; p.H = H; p.W = W;
     p.Ho = (H + stride - 1) / stride; p.Wo = (W + stride - 1) / stride;
     if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv3x3: stride-2 input must be even");
-    static const bool use_tc = [] { const char* e = getenv("MDS_CONV_TC"); return !(e && e[0] == '0'); }();
-    if (use_tc && cin == 32 && cmid == 128 && stride == 1 && cproj == 32 && res == 1)
+    if (cin == 32 && cmid == 128 && stride == 1 && cproj == 32 && res == 1)     // blocks.1.1: tcgen05 implicit GEMM
         return launch_conv3_tc<32, 128, 32>(in, out, w1, b1, w2, b2, n, H, W, st);
 #define C3CASE(CI, CM, S, CP, R, MB, MT) \
     if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0)) return launch_conv3_t<CI, CM, S, CP, R, MB, MT>(p, st);
@@ -340,8 +339,7 @@ static int launch_gemm(const __half* A, const __half* W, const float* bias, cons
                        const __half* bias_mat = nullptr) {
     if (K % 16 || N % 16 || K > 1152) return fail(MDS_ERR_INVALID, "gemm1x1: N, K must be multiples of 16, K <= 1152 (N=%d K=%d)", N, K);
     if (rows_per_img <= 0 || n_img <= 0) return MDS_OK;
-    static const bool use_tc = [] { const char* e = getenv("MDS_GEMM_TC"); return !(e && e[0] == '0'); }();
-    if (use_tc && bias_mat != nullptr && gate == nullptr && res == nullptr && K <= kTcMaxKB * kTcBK && rows_per_img * n_img < (1LL << 31) && tc_pick_bn(N) >= 32)
+    if (bias_mat != nullptr && gate == nullptr && res == nullptr && K <= kTcMaxKB * kTcBK && rows_per_img * n_img < (1LL << 31) && tc_pick_bn(N) >= 32)
         return launch_gemm_tc(A, W, bias_mat, C, rows_per_img * n_img, N, K, act, st);
     // The M-tile index lives in gridDim.y (<= 65535): split very large ungated problems into row slabs.
     const long long max_rows = 65535LL * kGemmBM;

@@ -101,6 +101,35 @@ def test_conv3x3(lib, cin, cmid, stride, cproj, res, hw):
     assert rel(nchw(out), ref) <= TOL
 
 
+def test_conv3x3_tcgen05_many_tiles(lib):
+    """blocks.1.1 at its real 184x320 resolution, 5 images: 650 halo tiles, so every persistent CTA loops over several tiles
+    and both tile buffers / both accumulators wrap their mbarrier phases."""
+    cin, cmid, cproj = 32, 128, 32
+    n, H, W = 5, 184, 320
+    x = h16(torch.randn(n, cin, H, W, generator=gen(1)))
+    w1 = h16(torch.randn(cmid, cin, 3, 3, generator=gen(2)) * (2.0 / (9 * cin)) ** 0.5)
+    b1 = torch.randn(cmid, generator=gen(3)) * 0.1
+    w2 = h16(torch.randn(cproj, cmid, generator=gen(4)) * (1.0 / cmid) ** 0.5)
+    b2 = torch.randn(cproj, generator=gen(5)) * 0.1
+    xf = x.float()
+    y = F.silu(F.conv2d(xf, w1.float(), b1, padding=1))
+    ref = F.conv2d(h16(y).float(), w2.float()[:, :, None, None], b2) + xf
+    d_x = nhwc(x).to(DEV)
+    d_w1 = w1.permute(0, 2, 3, 1).reshape(cmid, -1).contiguous().to(DEV)
+    d_b1, d_w2, d_b2 = b1.to(DEV), w2.contiguous().to(DEV), b2.to(DEV)
+    out = torch.zeros((n, H, W, cproj), dtype=torch.float16, device=DEV)
+    for _ in range(2):
+        ok(lib.mds_k_conv3x3(d_x.data_ptr(), out.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(), d_w2.data_ptr(), d_b2.data_ptr(),
+                             n, H, W, cin, cmid, 1, cproj, 1, None), lib)
+    torch.cuda.synchronize()
+    assert rel(nchw(out), ref) <= TOL
+    first = out.clone()
+    ok(lib.mds_k_conv3x3(d_x.data_ptr(), out.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(), d_w2.data_ptr(), d_b2.data_ptr(),
+                         n, H, W, cin, cmid, 1, cproj, 1, None), lib)
+    torch.cuda.synchronize()
+    assert torch.equal(first, out)
+
+
 GEMM_CASES = [  # (N, K, gated, res, act)
     (192, 48, 0, 0, 1), (96, 192, 1, 0, 0), (384, 96, 0, 0, 1), (96, 384, 1, 1, 0), (576, 96, 0, 0, 1),
     (112, 576, 1, 0, 0), (672, 112, 0, 0, 1), (112, 672, 1, 1, 0), (192, 672, 1, 0, 0), (1152, 192, 0, 0, 1),
