@@ -4,5 +4,6 @@ from .indexes import StackIndexesGenerator  # noqa: F401
 from .frames import get_frames_processor, PadNormalizeFramesProcessor  # noqa: F401
 from .model import MultiDimStacker  # noqa: F401
 from .predictor import MultiDimStackerPredictor, load_model  # noqa: F401
+from .train import FrozenEncoderTrainer  # noqa: F401
 
 nn_module_registry = {"multidim_stacker": MultiDimStacker}   # plug point of BallActionModel.nn_module (argus_models.py:18-21)

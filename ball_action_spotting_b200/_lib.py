@@ -20,6 +20,20 @@ class MdsFrames(C.Structure):
                 ("stored_h", C.c_int), ("pad_top", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hflip", C.c_int)]
 
 
+class MdsTrainConfig(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("num_classes", "num_frames", "stack_size", "num_3d_blocks", "num_3d_features",
+                                        "num_3d_stack_proj", "expansion_3d_ratio", "se_reduce_3d_ratio", "device", "amp",
+                                        "nesterov")] +
+                [(n, C.c_float) for n in ("drop_rate", "drop_path_rate", "focal_alpha", "focal_gamma", "momentum",
+                                          "init_scale")])
+
+
+class MdsTrainStepArgs(C.Structure):
+    _fields_ = [("enc_feats", C.c_void_p), ("targets", C.c_void_p), ("dp_masks", C.c_void_p), ("dropout_mask", C.c_void_p),
+                ("seed", C.c_ulonglong), ("b", C.c_int), ("fh", C.c_int), ("fw", C.c_int), ("lr", C.c_float),
+                ("apply_update", C.c_int), ("loss_out", C.c_void_p), ("logits_out", C.c_void_p)]
+
+
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _FP = C.POINTER(MdsFrames)
 
@@ -32,6 +46,7 @@ SIGNATURES = {
     "mds_weights_commit": (_i, [_vp]),
     "mds_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "mds_forward_2d": (_i, [_vp, _FP, _i, _vp, _vp, _sz, _vp]),
+    "mds_forward_encoder": (_i, [_vp, _FP, _i, _vp, _vp, _sz, _vp]),
     "mds_forward_3d": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mds_forward_head": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "mds_forward": (_i, [_vp, _FP, _i, _vp, _i, _vp, _sz, _vp]),
@@ -45,6 +60,17 @@ SIGNATURES = {
     "mds_k_gemm_gated": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mds_k_gem": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp]),
     "mds_k_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mds_train_create": (_i, [C.POINTER(MdsTrainConfig), C.POINTER(_vp)]),
+    "mds_train_destroy": (_i, [_vp]),
+    "mds_train_num_tensors": (_i, [_vp, _i]),
+    "mds_train_tensor_info": (_i, [_vp, _i, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong)]),
+    "mds_train_set": (_i, [_vp, C.c_char_p, _vp, C.c_longlong]),
+    "mds_train_get": (_i, [_vp, C.c_char_p, _i, _vp, C.c_longlong]),
+    "mds_train_commit": (_i, [_vp, _vp]),
+    "mds_train_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "mds_train_step": (_i, [_vp, C.POINTER(MdsTrainStepArgs), _vp, _sz, _vp]),
+    "mds_train_scaler_state": (_i, [_vp, _vp]),
+    "mds_train_batches_tracked": (C.c_longlong, [_vp]),
     "mds_launch_count": (C.c_longlong, [_i]),
     "mds_profile_begin": (_i, []),
     "mds_profile_end": (_i, [_vp, _vp, _vp, _i, _vp]),

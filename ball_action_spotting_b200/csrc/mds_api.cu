@@ -20,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "se_head.cuh"
 #include "stem.cuh"
+#include "train.cuh"
 
 using namespace mds;
 
@@ -719,7 +720,8 @@ static int check_ready(MdsHandle* h) {
     return MDS_OK;
 }
 
-static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __half* feats_out, Arena& ar, cudaStream_t st) {
+static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __half* feats_out, Arena& ar, cudaStream_t st,
+                           bool project = true) {
     if (fr.H % 32 || fr.W % 32 || fr.H <= 0 || fr.W <= 0)
         return fail(MDS_ERR_INVALID, "forward_2d: H (%d) and W (%d) must be positive multiples of 32", fr.H, fr.W);
     if (fr.stored_h + fr.pad_top > fr.H || fr.pad_top < 0 || fr.stored_h <= 0)
@@ -765,8 +767,13 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
             cur ^= 1; hh = ho; ww = wo;
         }
         ++g_prof_tag;
-        TRY(launch_gemm(X[cur], h->proj2d_w, h->proj2d_b, nullptr, nullptr, feats_out + (size_t)i0 * P * 192,
-                        (long long)P, cs, h->cfg.num_3d_features, 192, 1, st, h->proj2d_bm));
+        if (project) {
+            TRY(launch_gemm(X[cur], h->proj2d_w, h->proj2d_b, nullptr, nullptr, feats_out + (size_t)i0 * P * 192,
+                            (long long)P, cs, h->cfg.num_3d_features, 192, 1, st, h->proj2d_bm));
+        } else {      // frozen-encoder training: hand out the encoder output itself (input of conv2d_projection)
+            CUDA_TRY(cudaMemcpyAsync(feats_out + (size_t)i0 * P * 192, X[cur], (size_t)cs * P * 192 * sizeof(__half),
+                                     cudaMemcpyDeviceToDevice, st));
+        }
     }
     return MDS_OK;
 }
@@ -826,6 +833,15 @@ extern "C" int mds_forward_2d(MdsHandle* h, const MdsFrames* frames, int n_image
     DeviceGuard g(h->cfg.device);
     Arena ar(ws, ws_bytes);
     return forward_2d_impl(h, *frames, n_images, reinterpret_cast<__half*>(feats_out), ar, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mds_forward_encoder(MdsHandle* h, const MdsFrames* frames, int n_images, void* feats_out, void* ws,
+                                   size_t ws_bytes, void* stream) {
+    TRY(check_ready(h));
+    if (!frames || !frames->data || !feats_out || !ws) return fail(MDS_ERR_INVALID, "forward_encoder: null argument");
+    DeviceGuard g(h->cfg.device);
+    Arena ar(ws, ws_bytes);
+    return forward_2d_impl(h, *frames, n_images, reinterpret_cast<__half*>(feats_out), ar, reinterpret_cast<cudaStream_t>(stream), false);
 }
 
 extern "C" int mds_forward_3d(MdsHandle* h, const void* feats, int b, int fh, int fw, void* out, void* ws, size_t ws_bytes,
@@ -931,3 +947,5 @@ extern "C" int mds_k_linear(const float* feat, const float* w, const float* bias
                             int apply_sigmoid, void* stream) {
     return launch_linear(feat, w, bias, out, b, F, num_classes, apply_sigmoid, reinterpret_cast<cudaStream_t>(stream));
 }
+
+#include "train_api.inl"

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) gem_kernel(GemParams g) {
     const int t = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x;
     const int C8 = g.C >> 3;                 // threads along channels (8 ch each)
-    const int lanes_p = 256 / C8;            // position lanes
+    const int lanes_p = min(256 / C8, 8);    // position lanes (s_part holds 8)
     const int cg = tid % C8, pl = tid / C8;
     const bool cube = (g.p == 3.0f);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -112,6 +112,15 @@ class Engine:
                                       _stream(self.device)), "mds_forward_2d")
         return feats_out
 
+    def forward_encoder(self, desc: MdsFrames, n_images: int) -> torch.Tensor:
+        """conv2d_encoder(x)[-1] alone (multidim_stacker.py:215): fp16 (n_images, fh, fw, 192), input of conv2d_projection."""
+        fh, fw = desc.H // 32, desc.W // 32
+        feats = torch.empty((n_images, fh, fw, 192), dtype=torch.float16, device=self.device)
+        ws = self.workspace(desc.H, desc.W, n_images, 0)
+        check(self.lib.mds_forward_encoder(self._h, C.byref(desc), n_images, feats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           _stream(self.device)), "mds_forward_encoder")
+        return feats
+
     def forward_3d(self, feats: torch.Tensor) -> torch.Tensor:
         """feats fp16 (b, T, fh, fw, 192) contiguous -> fp16 (b, T, fh, fw, proj)."""
         b, T, fh, fw, c = feats.shape

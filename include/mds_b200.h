@@ -76,6 +76,11 @@ size_t mds_workspace_bytes(const MdsHandle* h, int H, int W, int n_images, int n
  * [n_images][H/32][W/32][192] (NHWC; the reference's (b, k, 192, h, w) with b*k = n_images). */
 int mds_forward_2d(MdsHandle* h, const MdsFrames* frames, int n_images, void* feats_out,
                    void* ws, size_t ws_bytes, void* stream);
+/* The frozen conv2d_encoder alone (multidim_stacker.py:215, `self.conv2d_encoder(x)[-1]`, eval mode): the input of
+ * conv2d_projection, fp16 [n_images][H/32][W/32][192].  Feeds the training step below (freeze_conv2d_encoder,
+ * src/argus_models.py:104-110). */
+int mds_forward_encoder(MdsHandle* h, const MdsFrames* frames, int n_images, void* feats_out, void* ws, size_t ws_bytes,
+                        void* stream);
 /* MultiDimStacker.forward_3d (multidim_stacker.py:221-230): feats fp16 [b][T][fh][fw][192] -> out fp16
  * [b][T][fh][fw][proj] (the reference's (b, proj*T, h, w) with channel = t*proj + c). */
 int mds_forward_3d(MdsHandle* h, const void* feats, int b, int fh, int fw, void* out, void* ws, size_t ws_bytes,
@@ -122,10 +127,57 @@ int mds_k_linear(const float* feat, const float* w, const float* bias, float* ou
  * blocks, 150 conv3d_projection, 200 head, -1 direct kernel call), stop recording. */
 typedef enum MdsKernelKind {
     MDS_KIND_STEM = 0, MDS_KIND_CONV3X3 = 1, MDS_KIND_GEMM1X1 = 2, MDS_KIND_DWCONV2D = 3, MDS_KIND_DWCONV3D = 4,
-    MDS_KIND_SE_FC = 5, MDS_KIND_HEAD = 6
+    MDS_KIND_SE_FC = 5, MDS_KIND_HEAD = 6,
+    /* training step: weight-gradient GEMMs, BatchNorm column kernels, depthwise 3x3x3 fwd/bwd, small kernels */
+    MDS_KIND_TRAIN_WGRAD = 7, MDS_KIND_TRAIN_BN = 8, MDS_KIND_TRAIN_DW = 9, MDS_KIND_TRAIN_SMALL = 10
 } MdsKernelKind;
 int mds_profile_begin(void);
 int mds_profile_end(int* kinds, int* tags, float* ms, int capacity, int* count);
+
+/* ---- training step with a frozen 2D encoder (BASELINE.json configs[4]) -------------------------------------------
+ * Replaces BallActionModel.train_step (src/argus_models.py:41-74) for configs with freeze_conv2d_encoder
+ * (configs/ball_action/ball_finetune_long_004.py:72): train-mode forward of conv2d_projection, the InvertedResidual3d
+ * blocks, conv3d_projection, GeM, dropout and the classifier (src/models/multidim_stacker.py:216-237), sigmoid focal
+ * loss (src/losses.py:31-48), backward, GradScaler (amp) and torch.optim.SGD with Nesterov momentum.  The trainer owns
+ * fp32 master parameters, gradients, momentum buffers and BatchNorm running statistics, all addressed by the reference's
+ * state_dict names; the caller owns inputs, outputs and the workspace. */
+typedef struct MdsTrainer MdsTrainer;
+typedef struct MdsTrainConfig {
+    int num_classes, num_frames, stack_size, num_3d_blocks, num_3d_features, num_3d_stack_proj, expansion_3d_ratio,
+        se_reduce_3d_ratio, device;
+    int amp;                 /* 1: dynamic loss scaling like torch.cuda.amp.GradScaler (argus_models.py:36), 0: scale 1 */
+    int nesterov;
+    float drop_rate, drop_path_rate;       /* multidim_stacker.py:150-151 */
+    float focal_alpha, focal_gamma;        /* src/losses.py:54-57 */
+    float momentum;
+    float init_scale;        /* <= 0: GradScaler default 65536 */
+} MdsTrainConfig;
+typedef struct MdsTrainStepArgs {
+    const void* enc_feats;       /* fp16 [b][T][fh][fw][192]: mds_forward_encoder output */
+    const float* targets;        /* f32 [b][num_classes] (soft labels allowed) */
+    const float* dp_masks;       /* f32 [num_3d_blocks][b], 0 or 1/keep (timm drop_path); NULL: drawn from seed */
+    const float* dropout_mask;   /* f32 [b][proj*T], 0 or 1/(1-p) (F.dropout); NULL: drawn from seed */
+    unsigned long long seed;
+    int b, fh, fw;
+    float lr;
+    int apply_update;            /* 0: forward + backward only (gradients stay readable through mds_train_get) */
+    float* loss_out;             /* device f32 [1], optional */
+    float* logits_out;           /* device f32 [b][num_classes], optional */
+} MdsTrainStepArgs;
+int mds_train_create(const MdsTrainConfig* cfg, MdsTrainer** out);
+int mds_train_destroy(MdsTrainer* t);
+/* kind 0: trainable parameters (reference parameter order), kind 1: BatchNorm running statistics */
+int mds_train_num_tensors(const MdsTrainer* t, int kind);
+int mds_train_tensor_info(const MdsTrainer* t, int kind, int i, const char** name, long long* numel);
+int mds_train_set(MdsTrainer* t, const char* name, const float* host, long long numel);
+/* what 0: value, 1: gradient of the last step (unscaled), 2: momentum buffer; synchronises the device */
+int mds_train_get(MdsTrainer* t, const char* name, int what, float* host, long long numel);
+int mds_train_commit(MdsTrainer* t, void* stream);     /* after mds_train_set: derive the fp16 GEMM operands */
+size_t mds_train_workspace_bytes(const MdsTrainer* t, int b, int fh, int fw);
+int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* args, void* ws, size_t ws_bytes, void* stream);
+/* host4: loss scale, growth tracker, found_inf flag, optimizer steps performed; synchronises the device */
+int mds_train_scaler_state(MdsTrainer* t, float* host4);
+long long mds_train_batches_tracked(const MdsTrainer* t);   /* BatchNorm num_batches_tracked increment */
 
 /* number of kernels launched by this library in the calling thread since the last reset (bench "gpu_launches") */
 long long mds_launch_count(int reset);
