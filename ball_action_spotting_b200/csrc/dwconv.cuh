@@ -18,8 +18,10 @@ struct DwParams {
     const __half* in;    // [n][T][H][W][C]
     __half* out;         // [n][T][Ho][Wo][C]
     const float* w;      // [taps][C]  tap = (dt*3 + r)*3 + s, BN scale folded
-    const float* bias;   // [C]
+    const float* bias;   // [C]   (LIN mode: the shift reference of the BatchNorm statistics, see below)
     float* partials;     // [n][nparts][C]  per-CTA sums over its part of (T,Ho,Wo) of the fp32 SiLU output (deterministic SE squeeze)
+                         // LIN mode (training): [n * nparts][2][C] sums of (y - ref) and (y - ref)^2 of the stored fp16
+                         // output, or nullptr
     int n, T, H, W, C, Ho, Wo;
     int rows_per_chunk, chunks, xtiles, slabs, nparts;
 };
@@ -39,7 +41,7 @@ struct DwCfg {
     static constexpr int NST = (KT == 3) ? 4 : (STRIDE == 2 ? 3 : 4);
     static constexpr int CHUNKS = KT * IW * 8;                               // 16-byte requests per input row
     static constexpr int SLOTS = (CHUNKS + 255) / 256;
-    static constexpr size_t SMEM = (size_t)NST * STAGE_HALVES * 2 + 8 * kDwCS * sizeof(float);
+    static constexpr size_t SMEM = (size_t)NST * STAGE_HALVES * 2 + 2 * 8 * kDwCS * sizeof(float);
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -49,7 +51,9 @@ __device__ __forceinline__ float2 lds_half2(uint32_t saddr) {
     return unpack_half2(u);
 }
 
-template <int KT, int STRIDE>
+// LIN = true (training, conv_dw alone): no bias / activation; the epilogue instead accumulates the BatchNorm batch
+// statistics of the stored output (sums of y - ref and (y - ref)^2, ref = p.bias) as per-CTA partials.
+template <int KT, int STRIDE, bool LIN = false>
 __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     using Cfg = DwCfg<KT, STRIDE>;
     static_assert(KT == 1 || STRIDE == 1, "3D depthwise is stride 1");
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
         cp_async_commit();
     }
 
-    float2 lsum = make_float2(0.f, 0.f);
+    float2 lsum = make_float2(0.f, 0.f), lsq = make_float2(0.f, 0.f);
     float2 a0[kDwPXW], a1[kDwPXW], a2[kDwPXW];
 #pragma unroll
     for (int j = 0; j < kDwPXW; ++j) a0[j] = a1[j] = a2[j] = make_float2(0.f, 0.f);
@@ -151,9 +155,18 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
 #pragma unroll
         for (int j = 0; j < kDwPXW; ++j) {
             if (px_ok[j]) {
-                const float ox = silu_f(acc[j].x + bias.x), oy = silu_f(acc[j].y + bias.y);
-                lsum.x += ox; lsum.y += oy;
-                *reinterpret_cast<uint32_t*>(o_ptr + j * pxC) = pack_half2(ox, oy);
+                if constexpr (LIN) {
+                    const uint32_t packed = pack_half2(acc[j].x, acc[j].y);
+                    const float2 r = unpack_half2(packed);
+                    const float dx = r.x - bias.x, dy = r.y - bias.y;
+                    lsum.x += dx; lsum.y += dy;
+                    lsq.x = fmaf(dx, dx, lsq.x); lsq.y = fmaf(dy, dy, lsq.y);
+                    *reinterpret_cast<uint32_t*>(o_ptr + j * pxC) = packed;
+                } else {
+                    const float ox = silu_f(acc[j].x + bias.x), oy = silu_f(acc[j].y + bias.y);
+                    lsum.x += ox; lsum.y += oy;
+                    *reinterpret_cast<uint32_t*>(o_ptr + j * pxC) = pack_half2(ox, oy);
+                }
             }
         }
         o_ptr += out_pitch;
@@ -227,15 +240,29 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     cp_async_wait<0>();
 
     // ---- SE squeeze: reduce the 8 warps' partial sums in a fixed order; one plain store per channel per CTA ----
+    if (LIN && p.partials == nullptr) return;
     s_part[warp * kDwCS + 2 * lane] = lsum.x;
     s_part[warp * kDwCS + 2 * lane + 1] = lsum.y;
+    if constexpr (LIN) {
+        s_part[8 * kDwCS + warp * kDwCS + 2 * lane] = lsq.x;
+        s_part[8 * kDwCS + warp * kDwCS + 2 * lane + 1] = lsq.y;
+    }
     __syncthreads();
+    const int part = blockIdx.y * p.xtiles + xt;       // (t, row chunk, column tile)
     if (tid < kDwCS && c_slab + tid < p.C) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += s_part[i * kDwCS + tid];
-        const int part = blockIdx.y * p.xtiles + xt;       // (t, row chunk, column tile)
-        p.partials[((size_t)n * p.nparts + part) * p.C + c_slab + tid] = s;
+        if constexpr (LIN) p.partials[(((size_t)n * p.nparts + part) * 2) * p.C + c_slab + tid] = s;
+        else p.partials[((size_t)n * p.nparts + part) * p.C + c_slab + tid] = s;
+    }
+    if constexpr (LIN) {
+        if (tid >= kDwCS && tid < 2 * kDwCS && c_slab + tid - kDwCS < p.C) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += s_part[8 * kDwCS + i * kDwCS + tid - kDwCS];
+            p.partials[(((size_t)n * p.nparts + part) * 2 + 1) * p.C + c_slab + tid - kDwCS] = s;
+        }
     }
 }
 

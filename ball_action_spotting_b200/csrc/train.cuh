@@ -7,6 +7,7 @@
 // no floating-point atomics, the step is bit-reproducible.
 #pragma once
 #include "common.cuh"
+#include "dwconv.cuh"
 
 namespace mds {
 
@@ -71,6 +72,9 @@ __device__ __forceinline__ void load8(const float* src, int cg, float (&v)[8]) {
 __device__ __forceinline__ void load_row8(const __half* t, size_t row, int C, int cg, float (&v)[8]) {
     half8_to_float(__ldg(reinterpret_cast<const uint4*>(t + row * C) + cg), v);
 }
+__device__ __forceinline__ uint4 ldg_row(const __half* t, size_t row, int C, int cg) {
+    return __ldg(reinterpret_cast<const uint4*>(t + row * C) + cg);
+}
 __device__ __forceinline__ void store_row8(__half* t, size_t row, int C, int cg, const float (&v)[8]) {
     *(reinterpret_cast<uint4*>(t + row * C) + cg) = float8_to_half(v);
 }
@@ -96,22 +100,34 @@ __device__ __forceinline__ void ew_reduce_store(const EwParams& p, const EwCtx& 
     }
 }
 
-// BatchNorm batch statistics: partial sums of (y - ref) and (y - ref)^2, ref = row 0 of the tensor (a shift that makes
-// the one-pass variance well conditioned).
+// BatchNorm batch statistics: partial sums of (y - ref) and (y - ref)^2, ref = p.mean = the layer's running mean (a
+// data-independent guess of the batch mean: the shift keeps the one-pass variance well conditioned).
 __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(EwParams p) {
     const EwCtx c = ew_ctx(p);
     float acc[2][8] = {};
     if (c.active) {
         float ref[8];
-        load_row8(p.y, 0, p.C, c.cg, ref);
-        for (int r = c.r0 + c.rl; r < c.r1; r += c.RL) {
+        load8(p.mean, c.cg, ref);
+        for (int r = c.r0 + c.rl; r < c.r1; r += 2 * c.RL) {        // two rows (four 16-byte loads per pair) in flight
+            const bool two = r + c.RL < c.r1;
+            const uint4 ra = ldg_row(p.y, c.base + r, p.C, c.cg);
+            const uint4 rb = two ? ldg_row(p.y, c.base + r + c.RL, p.C, c.cg) : make_uint4(0, 0, 0, 0);
             float v[8];
-            load_row8(p.y, c.base + r, p.C, c.cg, v);
+            half8_to_float(ra, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float d = v[i] - ref[i];
                 acc[0][i] += d;
                 acc[1][i] = fmaf(d, d, acc[1][i]);
+            }
+            if (two) {
+                half8_to_float(rb, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float d = v[i] - ref[i];
+                    acc[0][i] += d;
+                    acc[1][i] = fmaf(d, d, acc[1][i]);
+                }
             }
         }
     }
@@ -130,12 +146,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(EwParams p) {
         load8(p.shift, c.cg, sh);
         if (MODE == 2) load8(p.smul + (size_t)c.smp * p.C, c.cg, gt);
         const float bm = (MODE == 3 && p.bmul) ? __ldg(p.bmul + c.smp) : 1.0f;
-        for (int r = c.r0 + c.rl; r < c.r1; r += c.RL) {
+        auto row = [&](const uint4& ry, const uint4& rr, int r) {
             float v[8], o[8];
-            load_row8(p.y, c.base + r, p.C, c.cg, v);
+            half8_to_float(ry, v);
             if (MODE == 3) {
                 float res[8];
-                load_row8(p.g, c.base + r, p.C, c.cg, res);
+                half8_to_float(rr, res);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = fmaf(fmaf(v[i], sc[i], sh[i]), bm, res[i]);
             } else {
@@ -147,6 +163,16 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(EwParams p) {
                 }
             }
             if (MODE != 1) store_row8(p.out, c.base + r, p.C, c.cg, o);
+        };
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        for (int r = c.r0 + c.rl; r < c.r1; r += 2 * c.RL) {
+            const bool two = r + c.RL < c.r1;
+            const uint4 ya = ldg_row(p.y, c.base + r, p.C, c.cg);
+            const uint4 ga = MODE == 3 ? ldg_row(p.g, c.base + r, p.C, c.cg) : zero;
+            const uint4 yb = two ? ldg_row(p.y, c.base + r + c.RL, p.C, c.cg) : zero;
+            const uint4 gb = (two && MODE == 3) ? ldg_row(p.g, c.base + r + c.RL, p.C, c.cg) : zero;
+            row(ya, ga, r);
+            if (two) row(yb, gb, r + c.RL);
         }
     }
     if (MODE == 1) ew_reduce_store<1>(p, c, acc);
@@ -171,10 +197,10 @@ __device__ __forceinline__ void bwd_load_const(const EwParams& p, const EwCtx& c
     k.bm = p.bmul ? __ldg(p.bmul + c.smp) : 1.0f;
 }
 template <bool ACT>
-__device__ __forceinline__ void bwd_row(const EwParams& p, const EwCtx& c, const BwdConst& k, int r, float (&dz)[8], float (&yh)[8]) {
+__device__ __forceinline__ void bwd_row(const BwdConst& k, const uint4& ry, const uint4& rg, float (&dz)[8], float (&yh)[8]) {
     float v[8], g[8];
-    load_row8(p.y, c.base + r, p.C, c.cg, v);
-    load_row8(p.g, c.base + r, p.C, c.cg, g);
+    half8_to_float(ry, v);
+    half8_to_float(rg, g);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float da = g[i];
@@ -193,13 +219,26 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(EwParams p) {
     if (c.active) {
         BwdConst k;
         bwd_load_const(p, c, k);
-        for (int r = c.r0 + c.rl; r < c.r1; r += c.RL) {
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        for (int r = c.r0 + c.rl; r < c.r1; r += 2 * c.RL) {
+            const bool two = r + c.RL < c.r1;
+            const uint4 ya = ldg_row(p.y, c.base + r, p.C, c.cg), ga = ldg_row(p.g, c.base + r, p.C, c.cg);
+            const uint4 yb = two ? ldg_row(p.y, c.base + r + c.RL, p.C, c.cg) : zero;
+            const uint4 gb = two ? ldg_row(p.g, c.base + r + c.RL, p.C, c.cg) : zero;
             float dz[8], yh[8];
-            bwd_row<ACT>(p, c, k, r, dz, yh);
+            bwd_row<ACT>(k, ya, ga, dz, yh);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 acc[0][i] += dz[i];
                 acc[1][i] = fmaf(dz[i], yh[i], acc[1][i]);
+            }
+            if (two) {
+                bwd_row<ACT>(k, yb, gb, dz, yh);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[0][i] += dz[i];
+                    acc[1][i] = fmaf(dz[i], yh[i], acc[1][i]);
+                }
             }
         }
     }
@@ -217,12 +256,23 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(EwParams p) {
     load8(p.c1, c.cg, c1);
     load8(p.c2, c.cg, c2);
     load8(p.gr, c.cg, gr);
-    for (int r = c.r0 + c.rl; r < c.r1; r += c.RL) {
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int r = c.r0 + c.rl; r < c.r1; r += 2 * c.RL) {
+        const bool two = r + c.RL < c.r1;
+        const uint4 ya = ldg_row(p.y, c.base + r, p.C, c.cg), ga = ldg_row(p.g, c.base + r, p.C, c.cg);
+        const uint4 yb = two ? ldg_row(p.y, c.base + r + c.RL, p.C, c.cg) : zero;
+        const uint4 gb = two ? ldg_row(p.g, c.base + r + c.RL, p.C, c.cg) : zero;
         float dz[8], yh[8], o[8];
-        bwd_row<ACT>(p, c, k, r, dz, yh);
+        bwd_row<ACT>(k, ya, ga, dz, yh);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = gr[i] * (dz[i] - c1[i] - yh[i] * c2[i]);
         store_row8(p.out, c.base + r, p.C, c.cg, o);
+        if (two) {
+            bwd_row<ACT>(k, yb, gb, dz, yh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = gr[i] * (dz[i] - c1[i] - yh[i] * c2[i]);
+            store_row8(p.out, c.base + r + c.RL, p.C, c.cg, o);
+        }
     }
 }
 
@@ -273,7 +323,7 @@ __device__ __forceinline__ bool fin_reduce(const float* partials, int nparts, in
 
 struct BnFwdFin {
     const float* partials; int nparts;
-    const __half* y;              // row 0 = the shift reference used by bn_stats_kernel
+    const float* ref;             // [C] the shift the partial sums were taken against (read before running_mean is updated)
     const float *gamma, *beta;
     float *running_mean, *running_var;
     float *scale, *shift, *mean, *rstd;
@@ -285,7 +335,7 @@ __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(BnFwdFin f) {
     const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
     const double n = (double)f.count;
     const double d1 = tot[0] / n;
-    const double mean = (double)__half2float(f.y[ch]) + d1;
+    const double mean = (double)f.ref[ch] + d1;
     double var = tot[1] / n - d1 * d1;
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + (double)f.eps));
@@ -319,131 +369,171 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwdFin f) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Depthwise 3x3x3 convolution (conv_dw, multidim_stacker.py:110-113), forward / data gradient / weight gradient.
-// grid (C / 64, T, b), 8 warps; a warp walks rows of the (b, t) plane, a lane owns one channel pair, so every load
-// is one coalesced 128-byte line and the 27 neighbours are served by L1.
+// Depthwise 3x3x3 convolution (conv_dw, multidim_stacker.py:110-113).  Forward and data gradient run on the streaming
+// inference kernel (dwconv_kernel<3, 1, LIN>, dwconv.cuh) with tap-major weights; the data gradient correlates with
+// the mirrored kernel.  The weight gradient below uses the same CTA shape and cp.async ring.
 // ------------------------------------------------------------------------------------------------------------
-struct Dw3Params {
-    const __half* in;       // [b][T][H][W][C]
-    const __half* dy;       // wgrad: output gradient
-    __half* out;
-    const float* w;         // [C][27] (PyTorch layout of the (C,1,3,3,3) weight)
-    float* partials;        // wgrad: [b*T][27][C]
-    int T, H, W, C, flip;   // flip = 1: correlate with the mirrored kernel (data gradient)
-};
-
-__global__ void __launch_bounds__(256) dw3_fwd_kernel(Dw3Params p) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 64 + lane * 2;
-    const int t = blockIdx.y, b = blockIdx.z;
-    if (c >= p.C) return;
-    float2 w[27];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-        const int kk = p.flip ? 26 - k : k;
-        w[k] = make_float2(__ldg(p.w + (size_t)c * 27 + kk), __ldg(p.w + (size_t)(c + 1) * 27 + kk));
-    }
-    const size_t plane = (size_t)p.H * p.W * p.C;
-    const __half* in_b = p.in + (size_t)b * p.T * plane;
-    __half* out_bt = p.out + ((size_t)b * p.T + t) * plane;
-    for (int pos = warp; pos < p.H * p.W; pos += 8) {
-        const int h = pos / p.W, x = pos - h * p.W;
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) {
-            const int tt = t + dt - 1;
-            if (tt < 0 || tt >= p.T) continue;
-#pragma unroll
-            for (int dh = 0; dh < 3; ++dh) {
-                const int hh = h + dh - 1;
-                if (hh < 0 || hh >= p.H) continue;
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int xx = x + dx - 1;
-                    if (xx < 0 || xx >= p.W) continue;
-                    const float2 v = __half22float2(__ldg(reinterpret_cast<const __half2*>(
-                        in_b + (size_t)tt * plane + ((size_t)hh * p.W + xx) * p.C + c)));
-                    const float2 wk = w[(dt * 3 + dh) * 3 + dx];
-                    acc.x = fmaf(v.x, wk.x, acc.x);
-                    acc.y = fmaf(v.y, wk.y, acc.y);
-                }
-            }
-        }
-        *reinterpret_cast<__half2*>(out_bt + (size_t)pos * p.C + c) = __floats2half2_rn(acc.x, acc.y);
-    }
+// fp32 master weight [C][27] -> tap-major [27][C] and its mirror (tap 26 - k)
+__global__ void __launch_bounds__(256) dw3_weights_kernel(const float* src, float* w27, float* w27_flip, int C) {
+    const int i = blockIdx.x * 256 + threadIdx.x;      // i = k * C + c
+    if (i >= 27 * C) return;
+    const int k = i / C, c = i - k * C;
+    const float v = src[(size_t)c * 27 + k];
+    w27[i] = v;
+    w27_flip[(size_t)(26 - k) * C + c] = v;
 }
 
-// dW[c][tap] partial over one (b, t) plane: sum_pos dy[pos] * in[pos + offset(tap)]
-__global__ void __launch_bounds__(256) dw3_wgrad_kernel(Dw3Params p) {
-    __shared__ float s_acc[4][27][64];      // warps 4-7 add onto warps 0-3 (fixed order), then four-way sum
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 64 + lane * 2;
-    const int t = blockIdx.y, b = blockIdx.z;
+// dW[c][tap] = sum_pos dy[pos] * in[pos + offset(tap)].  CTA = (sample, plane t, 64-channel slab, row chunk); warp = 5
+// output columns, lane = one channel pair (packed f32x2).  A ring stage holds input row yi of the three planes
+// t-1, t, t+1 plus dy row yi + 1; the three dy rows an input row pairs with (yi+1, yi, yi-1 <-> kernel rows 0, 1, 2)
+// live in registers and shift by one per stage.  27 x 2 accumulators per thread, reduced over the 8 warps in a fixed
+// order into one partial per CTA.
+struct Dw3WgParams {
+    const __half* in;       // [n][T][H][W][C]  conv_dw input (silu(bn1(.)))
+    const __half* dy;       // [n][T][H][W][C]  gradient of the conv_dw output
+    float* partials;        // [n * gridDim.y * xtiles][27][C]
+    int n, T, H, W, C, rows_per_chunk, chunks, xtiles;
+};
+struct Dw3WgCfg {
+    static constexpr int IW = kDwTWX + 2, NV = kDwPXW + 2;
+    static constexpr int ROW_HALVES = IW * kDwCS;                       // one plane of one input row
+    static constexpr int DY_HALVES = kDwTWX * kDwCS;
+    static constexpr int STAGE_HALVES = 3 * ROW_HALVES + DY_HALVES;
+    static constexpr int NST = 4;
+    static constexpr int IN_CHUNKS = 3 * IW * 8, CHUNKS = IN_CHUNKS + kDwTWX * 8;
+    static constexpr int SLOTS = (CHUNKS + 255) / 256;
+    static constexpr size_t RING = (size_t)NST * STAGE_HALVES * 2;
+    static constexpr size_t RED = (size_t)8 * 27 * kDwCS * sizeof(float);
+    static constexpr size_t SMEM = RING > RED ? RING : RED;
+};
+
+__global__ void __launch_bounds__(256) dw3_wgrad_kernel(Dw3WgParams p) {
+    using Cfg = Dw3WgCfg;
+    extern __shared__ __align__(16) unsigned char dwg_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int xt = blockIdx.x % p.xtiles, slab = blockIdx.x / p.xtiles;
+    const int t = blockIdx.y / p.chunks, chunk = blockIdx.y - t * p.chunks;
+    const int n = blockIdx.z;
+    const int yo0 = chunk * p.rows_per_chunk, yo1 = min(p.H, yo0 + p.rows_per_chunk);
+    const int xo0 = xt * kDwTWX;
+    const int c_slab = slab * kDwCS;
+    const int yi0 = yo0 - 1, NR = (yo1 - yo0) + 2;
+    const size_t plane = (size_t)p.H * p.W * p.C;
+    const long long row_pitch = (long long)p.W * p.C;
+    const __half* in_n = p.in + (size_t)n * p.T * plane;
+    const __half* dy_nt = p.dy + ((size_t)n * p.T + t) * plane;
+
+    uint32_t s_off[Cfg::SLOTS];
+    const __half* g_ptr[Cfg::SLOTS];
+    bool s_ok[Cfg::SLOTS], s_dy[Cfg::SLOTS];
+#pragma unroll
+    for (int sl = 0; sl < Cfg::SLOTS; ++sl) {
+        const int idx = tid + sl * 256;
+        const bool is_dy = idx >= Cfg::IN_CHUNKS;
+        s_dy[sl] = is_dy;
+        if (!is_dy) {
+            const int pl = idx / (Cfg::IW * 8);
+            const int rem = idx - pl * (Cfg::IW * 8);
+            const int px = rem >> 3, c16 = rem & 7;
+            const int xi = xo0 + px - 1, ti = t + pl - 1, cc = c_slab + c16 * 8;
+            s_ok[sl] = (xi >= 0) && (xi < p.W) && (ti >= 0) && (ti < p.T) && (cc < p.C);
+            s_off[sl] = (uint32_t)(pl * Cfg::ROW_HALVES + px * kDwCS + c16 * 8) * 2u;
+            g_ptr[sl] = s_ok[sl] ? in_n + (long long)ti * (long long)plane + (long long)yi0 * row_pitch + (long long)xi * p.C + cc : p.in;
+        } else {
+            const int rem = idx - Cfg::IN_CHUNKS;
+            const int px = rem >> 3, c16 = rem & 7;
+            const int cc = c_slab + c16 * 8;
+            s_ok[sl] = (idx < Cfg::CHUNKS) && (xo0 + px < p.W) && (cc < p.C);
+            s_off[sl] = (uint32_t)(3 * Cfg::ROW_HALVES + px * kDwCS + c16 * 8) * 2u;
+            g_ptr[sl] = s_ok[sl] ? dy_nt + (long long)(yi0 + 1) * row_pitch + (long long)(xo0 + px) * p.C + cc : p.in;   // dy row yi + 1
+        }
+        if (idx >= Cfg::CHUNKS) s_off[sl] = 0xffffffffu;
+    }
+    const uint32_t ring_u32 = smem_u32(dwg_smem);
+    uint32_t iss_off = 0;
+    int iss_y = yi0;
+    auto issue = [&]() {
+        const bool in_ok = (unsigned)iss_y < (unsigned)p.H;
+        const bool dy_ok = (iss_y + 1 >= yo0) && (iss_y + 1 < yo1);      // only this chunk's output rows contribute here
+#pragma unroll
+        for (int sl = 0; sl < Cfg::SLOTS; ++sl) {
+            if (s_off[sl] != 0xffffffffu) {
+                const bool ok = (s_dy[sl] ? dy_ok : in_ok) && s_ok[sl];
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ring_u32 + iss_off + s_off[sl]),
+                             "l"(ok ? g_ptr[sl] : p.in), "r"(ok ? 16 : 0));
+                if (s_ok[sl]) g_ptr[sl] += row_pitch;
+            }
+        }
+        ++iss_y;
+        iss_off += Cfg::STAGE_HALVES * 2;
+        if (iss_off == Cfg::NST * Cfg::STAGE_HALVES * 2) iss_off = 0;
+    };
+#pragma unroll
+    for (int j = 0; j < Cfg::NST - 1; ++j) {
+        if (j < NR) issue();
+        cp_async_commit();
+    }
     float2 acc[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[k] = make_float2(0.f, 0.f);
-    const size_t plane = (size_t)p.H * p.W * p.C;
-    const __half* in_b = p.in + (size_t)b * p.T * plane;
-    const __half* dy_bt = p.dy + ((size_t)b * p.T + t) * plane;
-    if (c < p.C) {
-        for (int pos = warp; pos < p.H * p.W; pos += 8) {
-            const int h = pos / p.W, x = pos - h * p.W;
-            const float2 g = __half22float2(__ldg(reinterpret_cast<const __half2*>(dy_bt + (size_t)pos * p.C + c)));
+    float2 d0[kDwPXW], d1[kDwPXW], d2[kDwPXW];
 #pragma unroll
-            for (int dt = 0; dt < 3; ++dt) {
-                const int tt = t + dt - 1;
-                if (tt < 0 || tt >= p.T) continue;
+    for (int j = 0; j < kDwPXW; ++j) d0[j] = d1[j] = d2[j] = make_float2(0.f, 0.f);
+
+    uint32_t cons_off = 0;
+    const uint32_t in_base = ring_u32 + (uint32_t)(warp * kDwPXW * kDwCS + 2 * lane) * 2u;
+    const uint32_t dy_base = in_base + (uint32_t)(3 * Cfg::ROW_HALVES) * 2u;
+    for (int k = 0; k < NR; ++k) {
+        cp_async_wait<Cfg::NST - 2>();
+        __syncthreads();
+        if (k + Cfg::NST - 1 < NR) issue();
+        cp_async_commit();
 #pragma unroll
-                for (int dh = 0; dh < 3; ++dh) {
-                    const int hh = h + dh - 1;
-                    if (hh < 0 || hh >= p.H) continue;
+        for (int j = 0; j < kDwPXW; ++j) {
+            d0[j] = d1[j];
+            d1[j] = d2[j];
+            d2[j] = lds_half2(dy_base + cons_off + j * kDwCS * 2);
+        }
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int xx = x + dx - 1;
-                        if (xx < 0 || xx >= p.W) continue;
-                        const float2 v = __half22float2(__ldg(reinterpret_cast<const __half2*>(
-                            in_b + (size_t)tt * plane + ((size_t)hh * p.W + xx) * p.C + c)));
-                        const int k = (dt * 3 + dh) * 3 + dx;
-                        acc[k].x = fmaf(g.x, v.x, acc[k].x);
-                        acc[k].y = fmaf(g.y, v.y, acc[k].y);
-                    }
+        for (int dt = 0; dt < 3; ++dt) {
+            float2 v[Cfg::NV];
+#pragma unroll
+            for (int i = 0; i < Cfg::NV; ++i) v[i] = lds_half2(in_base + cons_off + (dt * Cfg::ROW_HALVES + i * kDwCS) * 2);
+#pragma unroll
+            for (int j = 0; j < kDwPXW; ++j)
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    acc[dt * 9 + 0 + s] = ffma2(d2[j], v[j + s], acc[dt * 9 + 0 + s]);
+                    acc[dt * 9 + 3 + s] = ffma2(d1[j], v[j + s], acc[dt * 9 + 3 + s]);
+                    acc[dt * 9 + 6 + s] = ffma2(d0[j], v[j + s], acc[dt * 9 + 6 + s]);
                 }
-            }
         }
+        cons_off += Cfg::STAGE_HALVES * 2;
+        if (cons_off == Cfg::NST * Cfg::STAGE_HALVES * 2) cons_off = 0;
     }
-    if (warp < 4) {
+    cp_async_wait<0>();
+    __syncthreads();                                   // the ring is dead: reuse it for the cross-warp reduction
+    float* s_acc = reinterpret_cast<float*>(dwg_smem);  // [8][27][64]
 #pragma unroll
-        for (int k = 0; k < 27; ++k) {
-            s_acc[warp][k][lane * 2] = acc[k].x;
-            s_acc[warp][k][lane * 2 + 1] = acc[k].y;
-        }
-    }
+    for (int k = 0; k < 27; ++k)
+        *reinterpret_cast<float2*>(s_acc + ((size_t)warp * 27 + k) * kDwCS + 2 * lane) = acc[k];
     __syncthreads();
-    if (warp >= 4) {
-#pragma unroll
-        for (int k = 0; k < 27; ++k) {
-            s_acc[warp - 4][k][lane * 2] += acc[k].x;
-            s_acc[warp - 4][k][lane * 2 + 1] += acc[k].y;
-        }
-    }
-    __syncthreads();
-    float* out = p.partials + ((size_t)b * p.T + t) * 27 * p.C;
-    for (int i = threadIdx.x; i < 27 * 64; i += 256) {
+    float* out = p.partials + (((size_t)n * gridDim.y + blockIdx.y) * p.xtiles + xt) * 27 * p.C;
+    for (int i = tid; i < 27 * kDwCS; i += 256) {
         const int k = i >> 6, cl = i & 63;
-        const int ch = blockIdx.x * 64 + cl;
-        if (ch >= p.C) continue;
-        float s = 0.f;
+        if (c_slab + cl >= p.C) continue;
+        float sum = 0.f;
 #pragma unroll
-        for (int wv = 0; wv < 4; ++wv) s += s_acc[wv][k][cl];
-        out[(size_t)k * p.C + ch] = s;
+        for (int wv = 0; wv < 8; ++wv) sum += s_acc[((size_t)wv * 27 + k) * kDwCS + cl];
+        out[(size_t)k * p.C + c_slab + cl] = sum;
     }
 }
-// grad[c][tap] = sum over planes of partials[plane][tap][c]
-__global__ void __launch_bounds__(256) dw3_wgrad_reduce_kernel(const float* partials, int nplanes, int C, float* grad) {
+// grad[c][tap] = sum over partials of partials[q][tap][c]
+__global__ void __launch_bounds__(256) dw3_wgrad_reduce_kernel(const float* partials, int nparts, int C, float* grad) {
     const int i = blockIdx.x * 256 + threadIdx.x;      // i = tap * C + c
     if (i >= 27 * C) return;
     float s = 0.f;
-    for (int q = 0; q < nplanes; ++q) s += partials[(size_t)q * 27 * C + i];
+    for (int q = 0; q < nparts; ++q) s += partials[(size_t)q * 27 * C + i];
     const int k = i / C, c = i - k * C;
     grad[(size_t)c * 27 + k] = s;
 }

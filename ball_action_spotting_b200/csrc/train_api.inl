@@ -30,6 +30,7 @@ struct TrainBlock {
     TrainGemmW pw, pwl;
     TrainBn bn1, bn2, bn3;
     size_t dw, se_w1, se_b1, se_w2, se_b2;
+    float *dw27, *dw27f;         // tap-major [27][mid] copy of conv_dw.weight and its mirror (data gradient)
 };
 
 struct MdsTrainer {
@@ -37,8 +38,9 @@ struct MdsTrainer {
     std::vector<TrainTensor> params, buffers;
     std::map<std::string, int> pindex, bindex;
     size_t n_params = 0, n_stats = 0;
-    float *P = nullptr, *G = nullptr, *Mom = nullptr, *S = nullptr, *scaler = nullptr, *bn_scratch = nullptr, *zeros = nullptr;
+    float *P = nullptr, *G = nullptr, *Mom = nullptr, *S = nullptr, *scaler = nullptr, *bn_scratch = nullptr, *zeros = nullptr, *dw27 = nullptr;
     __half* w16 = nullptr;
+    __half* zeros16 = nullptr;   // [1152][64] zero bias matrix of the tcgen05 GEMMs (no conv in this path has a bias)
     TrainGemmW proj2d, proj3d;
     TrainBn bn_p2d, bn_p3d;
     std::vector<TrainBlock> blocks;
@@ -132,6 +134,8 @@ extern "C" int mds_train_create(const MdsTrainConfig* cfg, MdsTrainer** out) {
     if (e == cudaSuccess) e = alloc((void**)&t->bn_scratch, bn_floats * 4);
     if (e == cudaSuccess) e = alloc((void**)&t->zeros, 1152 * 4);
     if (e == cudaSuccess) e = alloc((void**)&t->w16, w16_halves * 2);
+    if (e == cudaSuccess) e = alloc((void**)&t->zeros16, 1152 * 64 * 2);
+    if (e == cudaSuccess) e = alloc((void**)&t->dw27, (size_t)(cfg->num_3d_blocks > 0 ? cfg->num_3d_blocks : 1) * 2 * 27 * mid * 4);
     if (e != cudaSuccess) {
         mds_train_destroy(t);
         return fail(MDS_ERR_CUDA, "mds_train_create: %s", cudaGetErrorString(e));
@@ -142,7 +146,12 @@ extern "C" int mds_train_create(const MdsTrainConfig* cfg, MdsTrainer** out) {
         w.w16t = t->w16 + reinterpret_cast<size_t>(w.w16t);
     };
     rebase_bn(t->bn_p2d); rebase_bn(t->bn_p3d); rebase_w(t->proj2d); rebase_w(t->proj3d);
-    for (auto& b : t->blocks) { rebase_bn(b.bn1); rebase_bn(b.bn2); rebase_bn(b.bn3); rebase_w(b.pw); rebase_w(b.pwl); }
+    for (size_t i = 0; i < t->blocks.size(); ++i) {
+        TrainBlock& b = t->blocks[i];
+        rebase_bn(b.bn1); rebase_bn(b.bn2); rebase_bn(b.bn3); rebase_w(b.pw); rebase_w(b.pwl);
+        b.dw27 = t->dw27 + i * 2 * 27 * (size_t)mid;
+        b.dw27f = b.dw27 + 27 * (size_t)mid;
+    }
     const float init[4] = {cfg->amp ? (cfg->init_scale > 0.f ? cfg->init_scale : 65536.0f) : 1.0f, 0.f, 0.f, 0.f};
     cudaMemcpy(t->scaler, init, sizeof(init), cudaMemcpyHostToDevice);
     *out = t;
@@ -153,7 +162,7 @@ extern "C" int mds_train_destroy(MdsTrainer* t) {
     if (!t) return MDS_OK;
     DeviceGuard g(t->cfg.device);
     cudaFree(t->P); cudaFree(t->G); cudaFree(t->Mom); cudaFree(t->S); cudaFree(t->scaler); cudaFree(t->bn_scratch);
-    cudaFree(t->zeros); cudaFree(t->w16);
+    cudaFree(t->zeros); cudaFree(t->w16); cudaFree(t->dw27); cudaFree(t->zeros16);
     delete t;
     return MDS_OK;
 }
@@ -229,7 +238,11 @@ static int train_derive(MdsTrainer* t, cudaStream_t st) {
     };
     ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
     TRY(cast(t->proj2d));
-    for (auto& b : t->blocks) { TRY(cast(b.pw)); TRY(cast(b.pwl)); }
+    for (auto& b : t->blocks) {
+        TRY(cast(b.pw)); TRY(cast(b.pwl));
+        dw3_weights_kernel<<<(27 * t->mid() + 255) / 256, 256, 0, st>>>(t->P + b.dw, b.dw27, b.dw27f, t->mid());
+        LAUNCH_CHECK("dw3_weights");
+    }
     TRY(cast(t->proj3d));
     return MDS_OK;
 }
@@ -245,6 +258,16 @@ extern "C" int mds_train_commit(MdsTrainer* t, void* stream) {
 // --------------------------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------------------------
+// C[M][N] = A[M][K] W[N][K]^T (+ res): forward and data-gradient GEMMs of the 1x1x1 convolutions.  tcgen05 path of the
+// inference engine (gemm_tc.cuh): resident-A mode for K <= 192, streamed mode (one "image") for N <= 256; mma.sync otherwise.
+static int train_gemm(MdsTrainer* t, const __half* A, const __half* W, const __half* res, __half* C, long long M, int N, int K, cudaStream_t st) {
+    if (res == nullptr && K <= kTcMaxKB * kTcBK && tc_pick_bn(N) >= 32 && M < (1LL << 31))
+        return launch_gemm(A, W, t->zeros, nullptr, nullptr, C, M, 1, N, K, 0, st, t->zeros16);
+    if (N >= 32 && N <= 256 && N % 16 == 0 && K % 16 == 0 && M < (1LL << 31))
+        return launch_gemm_tc_stream(A, W, t->zeros16, res, C, (int)M, 1, N, K, 0, st);
+    return launch_gemm(A, W, t->zeros, res, nullptr, C, M, 1, N, K, 0, st);
+}
+
 constexpr int kTrainChunkRows = 128;
 static int train_chunks(int rows_per_sample) { return (rows_per_sample + kTrainChunkRows - 1) / kTrainChunkRows; }
 
@@ -256,22 +279,31 @@ static EwParams ew_base(const __half* y, int C, int rows_per_sample) {
 }
 static dim3 ew_grid(int rows_per_sample, int b) { return dim3(train_chunks(rows_per_sample), b); }
 
-// conv output y -> batch statistics -> scale / shift (+ running-stat update)
-static int train_bn_stats(MdsTrainer* t, const TrainBn& bn, const __half* y, int b, int rows_per_sample, float* partials, cudaStream_t st) {
+// batch statistics partials -> scale / shift (+ running-stat update).  `ref` = the per-channel shift the partial sums
+// were taken against (the running mean *before* this update: a cheap, data-independent guess of the batch mean that
+// keeps the one-pass variance well conditioned); the finalize kernel reads it before overwriting the running mean.
+static int train_bn_finalize(MdsTrainer* t, const TrainBn& bn, const float* partials, int nparts, double count, const float* ref, cudaStream_t st) {
     ProfScope ps(MDS_KIND_TRAIN_BN, st);
-    EwParams p = ew_base(y, bn.C, rows_per_sample);
-    p.partials = partials;
-    bn_stats_kernel<<<ew_grid(rows_per_sample, b), kEwThreads, 0, st>>>(p);
-    LAUNCH_CHECK("bn_stats");
     BnFwdFin f;
-    f.partials = partials; f.nparts = train_chunks(rows_per_sample) * b; f.y = y;
+    f.partials = partials; f.nparts = nparts; f.ref = ref;
     f.gamma = t->P + bn.gamma; f.beta = t->P + bn.beta;
     f.running_mean = t->S + bn.rm; f.running_var = t->S + bn.rv;
     f.scale = bn.scale(); f.shift = bn.shift(); f.mean = bn.mean(); f.rstd = bn.rstd();
-    f.C = bn.C; f.count = (float)((double)b * rows_per_sample); f.eps = 1e-5f; f.momentum = 0.1f;
+    f.C = bn.C; f.count = (float)count; f.eps = 1e-5f; f.momentum = 0.1f;
     bn_fwd_finalize_kernel<<<(bn.C + 31) / 32, 256, 0, st>>>(f);
     LAUNCH_CHECK("bn_fwd_finalize");
     return MDS_OK;
+}
+// conv output y -> batch statistics -> scale / shift
+static int train_bn_stats(MdsTrainer* t, const TrainBn& bn, const __half* y, int b, int rows_per_sample, float* partials, cudaStream_t st) {
+    {
+        ProfScope ps(MDS_KIND_TRAIN_BN, st);
+        EwParams p = ew_base(y, bn.C, rows_per_sample);
+        p.partials = partials; p.mean = t->S + bn.rm;
+        bn_stats_kernel<<<ew_grid(rows_per_sample, b), kEwThreads, 0, st>>>(p);
+        LAUNCH_CHECK("bn_stats");
+    }
+    return train_bn_finalize(t, bn, partials, train_chunks(rows_per_sample) * b, (double)b * rows_per_sample, t->S + bn.rm, st);
 }
 
 template <int MODE>
@@ -336,23 +368,69 @@ static int train_wgrad(const __half* dY, const __half* X, long long M, int N, in
     return MDS_OK;
 }
 
-static int train_dw3(const __half* in, const __half* dy, __half* out, const float* w, float* partials, float* grad, int b, int T, int H,
-                     int W, int C, int mode, cudaStream_t st) {
-    if (C % 64) return fail(MDS_ERR_INVALID, "dw3 (train): C must be a multiple of 64");
-    if (b > 65535 || T > 65535) return fail(MDS_ERR_INVALID, "dw3 (train): b / T too large");
-    ProfScope ps(MDS_KIND_TRAIN_DW, st);
-    Dw3Params p;
-    p.in = in; p.dy = dy; p.out = out; p.w = w; p.partials = partials; p.T = T; p.H = H; p.W = W; p.C = C; p.flip = mode == 1;
-    const dim3 grid(C / 64, T, b);
-    if (mode == 2) {
-        dw3_wgrad_kernel<<<grid, 256, 0, st>>>(p);
-        LAUNCH_CHECK("dw3_wgrad");
-        dw3_wgrad_reduce_kernel<<<(27 * C + 255) / 256, 256, 0, st>>>(partials, b * T, C, grad);
-        LAUNCH_CHECK("dw3_wgrad_reduce");
-    } else {
-        dw3_fwd_kernel<<<grid, 256, 0, st>>>(p);
-        LAUNCH_CHECK("dw3_fwd");
+// conv_dw forward / data gradient on the streaming inference kernel in LIN mode: w27 tap-major weights (mirrored for the
+// data gradient); stats (optional): per-CTA BatchNorm partial sums relative to `ref`, *nparts_total of them
+static int train_dw3_conv(const __half* in, __half* out, const float* w27, const float* ref, float* stats, int* nparts_total, int b, int T,
+                          int H, int W, int C, cudaStream_t st) {
+    if (C % 8 || b > 65535) return fail(MDS_ERR_INVALID, "dw3 (train): C must be a multiple of 8, b <= 65535");
+    DwParams p;
+    p.in = in; p.out = out; p.w = w27; p.bias = ref; p.partials = stats;
+    p.n = b; p.T = T; p.H = H; p.W = W; p.C = C; p.Ho = H; p.Wo = W;
+    p.xtiles = (W + kDwTWX - 1) / kDwTWX;
+    p.slabs = (C + kDwCS - 1) / kDwCS;
+    int chunks = 1;
+    const long long base = (long long)p.xtiles * p.slabs * b * T;
+    const long long want = (long long)num_sms() * 6;
+    if (base < want) {
+        chunks = (int)((want + base - 1) / base);
+        const int max_chunks = H / 6 > 0 ? H / 6 : 1;
+        if (chunks > max_chunks) chunks = max_chunks;
     }
+    p.rows_per_chunk = (H + chunks - 1) / chunks;
+    p.chunks = (H + p.rows_per_chunk - 1) / p.rows_per_chunk;
+    p.nparts = p.chunks * T * p.xtiles;
+    if (nparts_total) *nparts_total = p.nparts * b;
+    using Cfg = DwCfg<3, 1>;
+    auto kern = dwconv_kernel<3, 1, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    ProfScope ps(MDS_KIND_TRAIN_DW, st);
+    kern<<<dim3(p.xtiles * p.slabs, p.chunks * T, b), 256, Cfg::SMEM, st>>>(p);
+    LAUNCH_CHECK("dwconv_lin");
+    return MDS_OK;
+}
+static int dw3_wgrad_geometry(int b, int T, int H, int W, int C, int* chunks, int* rows) {
+    const int xtiles = (W + kDwTWX - 1) / kDwTWX, slabs = (C + kDwCS - 1) / kDwCS;
+    const long long base = (long long)xtiles * slabs * b * T;
+    int ch = (int)((2LL * num_sms() + base - 1) / base);
+    const int max_ch = H / 4 > 0 ? H / 4 : 1;
+    if (ch > max_ch) ch = max_ch;
+    if (ch < 1) ch = 1;
+    const int r = (H + ch - 1) / ch;
+    ch = (H + r - 1) / r;
+    if (chunks) *chunks = ch;
+    if (rows) *rows = r;
+    return b * T * ch * xtiles;       // partials per channel
+}
+static int train_dw3_wgrad(const __half* in, const __half* dy, float* partials, float* grad, int b, int T, int H, int W, int C, cudaStream_t st) {
+    if (C % 8 || b > 65535) return fail(MDS_ERR_INVALID, "dw3 wgrad: C must be a multiple of 8, b <= 65535");
+    Dw3WgParams p;
+    p.in = in; p.dy = dy; p.partials = partials; p.n = b; p.T = T; p.H = H; p.W = W; p.C = C;
+    p.xtiles = (W + kDwTWX - 1) / kDwTWX;
+    const int nparts = dw3_wgrad_geometry(b, T, H, W, C, &p.chunks, &p.rows_per_chunk);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(dw3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Dw3WgCfg::SMEM));
+        attr_set = true;
+    }
+    ProfScope ps(MDS_KIND_TRAIN_DW, st);
+    dw3_wgrad_kernel<<<dim3(p.xtiles * ((C + kDwCS - 1) / kDwCS), p.chunks * T, b), 256, Dw3WgCfg::SMEM, st>>>(p);
+    LAUNCH_CHECK("dw3_wgrad");
+    dw3_wgrad_reduce_kernel<<<(27 * C + 255) / 256, 256, 0, st>>>(partials, nparts, C, grad);
+    LAUNCH_CHECK("dw3_wgrad_reduce");
     return MDS_OK;
 }
 
@@ -365,7 +443,8 @@ struct TrainWs {
     float *partials, *wpart, *dwpart, *se_s, *se_h, *se_g, *se_dg, *se_dh, *se_sadd, *dp_mask, *do_mask;
     float *feat, *pooled, *mlog, *coef;
 };
-static int train_ws_take(const MdsTrainer* t, int b, int P, Arena& ar, TrainWs& w) {
+static int train_ws_take(const MdsTrainer* t, int b, int fh, int fw, Arena& ar, TrainWs& w) {
+    const int P = fh * fw;
     const int T = t->T(), c3 = t->cfg.num_3d_features, mid = t->mid(), rd = t->rd(), pj = t->cfg.num_3d_stack_proj;
     const int nb = (int)t->blocks.size();
     const size_t M = (size_t)b * T * P;
@@ -388,7 +467,7 @@ static int train_ws_take(const MdsTrainer* t, int b, int P, Arena& ar, TrainWs& 
     auto upd = [&](int N, int K) { size_t f = wgrad_partial_floats((long long)M, N, K, nullptr, nullptr); if (f > wp) wp = f; };
     upd(c3, 192); upd(mid, c3); upd(c3, mid); upd(pj, c3);
     w.wpart = ar.take<float>(wp);
-    w.dwpart = ar.take<float>((size_t)b * T * 27 * mid);
+    w.dwpart = ar.take<float>((size_t)dw3_wgrad_geometry(b, T, fh, fw, mid, nullptr, nullptr) * 27 * mid);
     w.se_s = ar.take<float>((size_t)nb * b * mid); w.se_h = ar.take<float>((size_t)nb * b * rd); w.se_g = ar.take<float>((size_t)nb * b * mid);
     w.se_dg = ar.take<float>((size_t)b * mid); w.se_dh = ar.take<float>((size_t)b * rd); w.se_sadd = ar.take<float>((size_t)b * mid);
     w.dp_mask = ar.take<float>((size_t)(nb > 0 ? nb : 1) * b); w.do_mask = ar.take<float>((size_t)b * t->F());
@@ -401,7 +480,7 @@ extern "C" size_t mds_train_workspace_bytes(const MdsTrainer* t, int b, int fh, 
     if (!t || b <= 0 || fh <= 0 || fw <= 0) return 0;
     Arena ar(nullptr, ~size_t(0) >> 1);
     TrainWs w;
-    train_ws_take(t, b, fh * fw, ar, w);
+    train_ws_take(t, b, fh, fw, ar, w);
     return ar.off + 4096;
 }
 
@@ -419,7 +498,7 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
     const int F = t->F(), K = t->cfg.num_classes;
     Arena ar(ws, ws_bytes);
     TrainWs w;
-    if (train_ws_take(t, b, P, ar, w)) return fail(MDS_ERR_WORKSPACE, "train_step: workspace too small (%zu bytes)", ws_bytes);
+    if (train_ws_take(t, b, a->fh, a->fw, ar, w)) return fail(MDS_ERR_WORKSPACE, "train_step: workspace too small (%zu bytes)", ws_bytes);
     const __half* xe = reinterpret_cast<const __half*>(a->enc_feats);
     const float inv_rows = 1.0f / (float)rows;
     const size_t se_smem = (size_t)(2 * mid + 2 * rd) * sizeof(float);
@@ -440,18 +519,21 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
 
     // ================================================= forward =================================================
     g_prof_tag = 300;
-    TRY(launch_gemm(xe, t->proj2d.w16, t->zeros, nullptr, nullptr, w.y0, M, 1, c3, 192, 0, st));            // multidim_stacker.py:216
+    TRY(train_gemm(t, xe, t->proj2d.w16, nullptr, w.y0, M, c3, 192, st));            // multidim_stacker.py:216
     TRY(train_bn_stats(t, t->bn_p2d, w.y0, b, rows, w.partials, st));
     TRY(train_bn_fwd<0>(t->bn_p2d, w.y0, nullptr, w.x[0], nullptr, nullptr, nullptr, b, rows, st));
     for (int i = 0; i < nb; ++i) {                                                                           // InvertedResidual3d.forward (:124-134)
         const TrainBlock& B = t->blocks[i];
         g_prof_tag = 301 + i;
         float* se_s = w.se_s + (size_t)i * b * mid; float* se_h = w.se_h + (size_t)i * b * rd; float* se_g = w.se_g + (size_t)i * b * mid;
-        TRY(launch_gemm(w.x[i], B.pw.w16, t->zeros, nullptr, nullptr, w.y1[i], M, 1, mid, c3, 0, st));
+        TRY(train_gemm(t, w.x[i], B.pw.w16, nullptr, w.y1[i], M, mid, c3, st));
         TRY(train_bn_stats(t, B.bn1, w.y1[i], b, rows, w.partials, st));
         TRY(train_bn_fwd<0>(B.bn1, w.y1[i], nullptr, w.a1[i], nullptr, nullptr, nullptr, b, rows, st));
-        TRY(train_dw3(w.a1[i], nullptr, w.y2[i], t->P + B.dw, nullptr, nullptr, b, T, a->fh, a->fw, mid, 0, st));
-        TRY(train_bn_stats(t, B.bn2, w.y2[i], b, rows, w.partials, st));
+        {   // conv_dw with the bn2 batch statistics accumulated in its epilogue
+            int nparts = 0;
+            TRY(train_dw3_conv(w.a1[i], w.y2[i], B.dw27, t->S + B.bn2.rm, w.partials, &nparts, b, T, a->fh, a->fw, mid, st));
+            TRY(train_bn_finalize(t, B.bn2, w.partials, nparts, (double)M, t->S + B.bn2.rm, st));
+        }
         TRY(train_bn_fwd<1>(B.bn2, w.y2[i], nullptr, nullptr, w.partials, nullptr, nullptr, b, rows, st));   // SE squeeze sums
         {
             ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
@@ -464,12 +546,12 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
             LAUNCH_CHECK("se_train_fwd");
         }
         TRY(train_bn_fwd<2>(B.bn2, w.y2[i], nullptr, w.a2g[i], nullptr, se_g, nullptr, b, rows, st));
-        TRY(launch_gemm(w.a2g[i], B.pwl.w16, t->zeros, nullptr, nullptr, w.y3[i], M, 1, c3, mid, 0, st));
+        TRY(train_gemm(t, w.a2g[i], B.pwl.w16, nullptr, w.y3[i], M, c3, mid, st));
         TRY(train_bn_stats(t, B.bn3, w.y3[i], b, rows, w.partials, st));
         TRY(train_bn_fwd<3>(B.bn3, w.y3[i], w.x[i], w.x[i + 1], nullptr, nullptr, dp_mask ? dp_mask + (size_t)i * b : nullptr, b, rows, st));
     }
     g_prof_tag = 350;
-    TRY(launch_gemm(w.x[nb], t->proj3d.w16, t->zeros, nullptr, nullptr, w.yp, M, 1, pj, c3, 0, st));         // :227
+    TRY(train_gemm(t, w.x[nb], t->proj3d.w16, nullptr, w.yp, M, pj, c3, st));         // :227
     TRY(train_bn_stats(t, t->bn_p3d, w.yp, b, rows, w.partials, st));
     TRY(train_bn_fwd<0>(t->bn_p3d, w.yp, nullptr, w.ap, nullptr, nullptr, nullptr, b, rows, st));
     g_prof_tag = 360;
@@ -499,7 +581,7 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
     TRY(train_wgrad(w.dP2, w.x[nb], M, pj, c3, w.wpart, t->G + t->proj3d.off, st));
     __half* dX = w.dXa;      // gradient with respect to the current block output
     __half* dXn = w.dXb;
-    TRY(launch_gemm(w.dP2, t->proj3d.w16t, t->zeros, nullptr, nullptr, dX, M, 1, c3, pj, 0, st));
+    TRY(train_gemm(t, w.dP2, t->proj3d.w16t, nullptr, dX, M, c3, pj, st));
     for (int i = nb - 1; i >= 0; --i) {
         const TrainBlock& B = t->blocks[i];
         g_prof_tag = 401 + i;
@@ -507,7 +589,7 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
         // bn3 (no activation), DropPath mask on the branch
         TRY(train_bn_bwd(t, B.bn3, false, w.y3[i], dX, w.D3, nullptr, nullptr, dp_mask ? dp_mask + (size_t)i * b : nullptr, b, rows, w.partials, st));
         TRY(train_wgrad(w.D3, w.a2g[i], M, c3, mid, w.wpart, t->G + B.pwl.off, st));
-        TRY(launch_gemm(w.D3, B.pwl.w16t, t->zeros, nullptr, nullptr, w.DM1, M, 1, mid, c3, 0, st));         // d (a2 * gate)
+        TRY(train_gemm(t, w.D3, B.pwl.w16t, nullptr, w.DM1, M, mid, c3, st));         // d (a2 * gate)
         {   // SE backward: d gate -> d squeeze, parameter gradients
             ProfScope ps(MDS_KIND_TRAIN_BN, st);
             EwParams p = ew_base(w.y2[i], mid, rows);
@@ -533,11 +615,11 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
             LAUNCH_CHECK("se_train_wgrad");
         }
         TRY(train_bn_bwd(t, B.bn2, true, w.y2[i], w.DM1, w.DM2, se_g, w.se_sadd, nullptr, b, rows, w.partials, st));   // -> d y2
-        TRY(train_dw3(w.a1[i], w.DM2, nullptr, nullptr, w.dwpart, t->G + B.dw, b, T, a->fh, a->fw, mid, 2, st));
-        TRY(train_dw3(w.DM2, nullptr, w.DM1, t->P + B.dw, nullptr, nullptr, b, T, a->fh, a->fw, mid, 1, st));          // -> d a1
+        TRY(train_dw3_wgrad(w.a1[i], w.DM2, w.dwpart, t->G + B.dw, b, T, a->fh, a->fw, mid, st));
+        TRY(train_dw3_conv(w.DM2, w.DM1, B.dw27f, t->zeros, nullptr, nullptr, b, T, a->fh, a->fw, mid, st));           // -> d a1
         TRY(train_bn_bwd(t, B.bn1, true, w.y1[i], w.DM1, w.DM2, nullptr, nullptr, nullptr, b, rows, w.partials, st));  // -> d y1
         TRY(train_wgrad(w.DM2, w.x[i], M, mid, c3, w.wpart, t->G + B.pw.off, st));
-        TRY(launch_gemm(w.DM2, B.pw.w16t, t->zeros, dX, nullptr, dXn, M, 1, c3, mid, 0, st));                // + shortcut gradient
+        TRY(train_gemm(t, w.DM2, B.pw.w16t, dX, dXn, M, c3, mid, st));                // + shortcut gradient
         __half* tmp = dX; dX = dXn; dXn = tmp;
     }
     g_prof_tag = 400;
