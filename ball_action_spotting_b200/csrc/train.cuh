@@ -295,27 +295,28 @@ __global__ void __launch_bounds__(kEwThreads) dgate_kernel(EwParams p) {
     ew_reduce_store<1>(p, c, acc);
 }
 
-// ---- finalize kernels: fixed-order reduction of the per-CTA partials, 32 channels per CTA --------------------
+// ---- finalize kernels: fixed-order reduction of the per-CTA partials, 8 channels per CTA, 128 part lanes ----------
+constexpr int kFinCh = 8, kFinLanes = 128, kFinThreads = kFinCh * kFinLanes;
 template <int NACC>
 __device__ __forceinline__ bool fin_reduce(const float* partials, int nparts, int C, double (&tot)[NACC]) {
-    __shared__ float s_p[8][NACC][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ch = blockIdx.x * 32 + lane;
+    __shared__ float s_p[NACC][kFinCh][kFinLanes + 1];
+    const int cl = threadIdx.x & (kFinCh - 1), pl = threadIdx.x / kFinCh;
+    const int ch = blockIdx.x * kFinCh + cl;
     float a[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) a[i] = 0.f;
     if (ch < C)
-        for (int q = warp; q < nparts; q += 8)
+        for (int q = pl; q < nparts; q += kFinLanes)
 #pragma unroll
             for (int i = 0; i < NACC; ++i) a[i] += partials[((size_t)q * NACC + i) * C + ch];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) s_p[warp][i][lane] = a[i];
+    for (int i = 0; i < NACC; ++i) s_p[i][cl][pl] = a[i];
     __syncthreads();
-    if (warp != 0 || ch >= C) return false;
+    if (threadIdx.x >= kFinCh || ch >= C) return false;
 #pragma unroll
     for (int i = 0; i < NACC; ++i) {
         double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += (double)s_p[w][i][lane];
+        for (int l = 0; l < kFinLanes; ++l) s += (double)s_p[i][cl][l];
         tot[i] = s;
     }
     return true;
@@ -329,10 +330,10 @@ struct BnFwdFin {
     float *scale, *shift, *mean, *rstd;
     int C; float count, eps, momentum;
 };
-__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(BnFwdFin f) {
+__global__ void __launch_bounds__(kFinThreads) bn_fwd_finalize_kernel(BnFwdFin f) {
     double tot[2];
     if (!fin_reduce<2>(f.partials, f.nparts, f.C, tot)) return;
-    const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ch = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1));
     const double n = (double)f.count;
     const double d1 = tot[0] / n;
     const double mean = (double)f.ref[ch] + d1;
@@ -357,10 +358,16 @@ struct BnBwdFin {
     float *c1, *c2, *gr;
     int C; float count;
 };
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwdFin f) {
+// per-sample column sums: out[b][c] = scale * sum_q partials[b][q][c]   (SE squeeze, d gate); grid (C / kFinCh, b)
+__global__ void __launch_bounds__(kFinThreads) colsum_finalize_kernel(const float* partials, int nparts, int C, float scale, float* out) {
+    double tot[1];
+    if (!fin_reduce<1>(partials + (size_t)blockIdx.y * nparts * C, nparts, C, tot)) return;
+    out[(size_t)blockIdx.y * C + blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1))] = (float)tot[0] * scale;
+}
+__global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(BnBwdFin f) {
     double tot[2];
     if (!fin_reduce<2>(f.partials, f.nparts, f.C, tot)) return;
-    const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ch = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1));
     f.dbeta[ch] = (float)tot[0];
     f.dgamma[ch] = (float)tot[1];
     f.c1[ch] = (float)(tot[0] / (double)f.count);
@@ -646,9 +653,9 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* partials
 // Squeeze-and-excitation, train mode (multidim_stacker.py:85-90): forward saves what the backward needs
 // ------------------------------------------------------------------------------------------------------------
 struct SeTrainParams {
-    const float* partials; int nparts;     // [b][nparts][C] column sums from bn_fwd_kernel<1> / dgate_kernel
+    const float* sums;                      // fwd: squeeze s[b][C] (mean of silu(bn2)); bwd: d gate[b][C] (colsum_finalize_kernel)
     const float *w1, *b1, *w2, *b2;         // conv_reduce [rd][C], [rd]; conv_expand [C][rd], [C]
-    float *s, *hpre, *gate;                 // saved: [b][C], [b][rd], [b][C]
+    float *hpre, *gate;                     // saved by the forward: [b][rd], [b][C]
     float *dgpre, *dhpre, *sadd;            // backward outputs: [b][C], [b][rd], [b][C]
     int C, rd; float inv_count;
 };
@@ -658,13 +665,7 @@ __global__ void __launch_bounds__(256) se_train_fwd_kernel(SeTrainParams p) {
     float* s_s = s_se;
     float* s_h = s_se + p.C;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int c = tid; c < p.C; c += 256) {
-        float s = 0.f;
-        for (int q = 0; q < p.nparts; ++q) s += p.partials[((size_t)b * p.nparts + q) * p.C + c];
-        s *= p.inv_count;
-        s_s[c] = s;
-        p.s[(size_t)b * p.C + c] = s;
-    }
+    for (int c = tid; c < p.C; c += 256) s_s[c] = p.sums[(size_t)b * p.C + c];
     __syncthreads();
     for (int j = warp; j < p.rd; j += 8) {
         float a = 0.f;
@@ -683,17 +684,15 @@ __global__ void __launch_bounds__(256) se_train_fwd_kernel(SeTrainParams p) {
         p.gate[(size_t)b * p.C + c] = sigmoid_f(a);
     }
 }
-// grid b: d gate (from dgate_kernel partials) -> d(pre-sigmoid), d(pre-SiLU hidden), d squeeze / row count
+// grid b: d gate -> d(pre-sigmoid), d(pre-SiLU hidden), d squeeze / row count
 __global__ void __launch_bounds__(256) se_train_bwd_kernel(SeTrainParams p) {
     extern __shared__ float s_se[];
     float* s_dg = s_se;             // [C] d gpre
     float* s_dh = s_se + p.C;       // [rd] d hpre
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int c = tid; c < p.C; c += 256) {
-        float s = 0.f;
-        for (int q = 0; q < p.nparts; ++q) s += p.partials[((size_t)b * p.nparts + q) * p.C + c];
         const float g = p.gate[(size_t)b * p.C + c];
-        const float d = s * g * (1.0f - g);
+        const float d = p.sums[(size_t)b * p.C + c] * g * (1.0f - g);
         s_dg[c] = d;
         p.dgpre[(size_t)b * p.C + c] = d;
     }
@@ -753,22 +752,26 @@ __global__ void __launch_bounds__(256) se_train_wgrad_kernel(SeGradParams p) {
 // ------------------------------------------------------------------------------------------------------------
 // Head: GeM with learnable p (multidim_stacker.py:20-45), dropout, classifier, focal loss (src/losses.py:31-48)
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kGemChunks = 8;       // CTAs per (sample, t) plane in the GeM kernels
 struct GemTrainParams {
     const __half* x;        // [b][T][P][C] = silu(bn(conv3d_projection))
     const float* p;         // device scalar (global_pool.p)
-    float *feat, *pooled, *mlog;   // [b][T*C]: mean^(1/p), mean of c^p, mean of c^p * ln c   (c = max(x, eps))
+    float* partials;        // [b][T][kGemChunks][2][C]: sums of c^p and c^p * ln c   (c = max(x, eps))
     int T, P, C; float eps;
 };
+// grid (T, b, kGemChunks)
 __global__ void __launch_bounds__(256) gem_train_fwd_kernel(GemTrainParams g) {
     __shared__ float s_part[2][8][260];
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int C8 = g.C >> 3, lanes_p = min(256 / C8, 8);
     const int cg = tid % C8, pl = tid / C8;
     const float pw = __ldg(g.p);
+    const int per = (g.P + kGemChunks - 1) / kGemChunks;
+    const int p0 = blockIdx.z * per, p1 = min(g.P, p0 + per);
     float acc[8] = {}, accl[8] = {};
     const __half* base = g.x + (((size_t)b * g.T + t) * g.P) * g.C + cg * 8;
     if (pl < lanes_p) {
-        for (int pos = pl; pos < g.P; pos += lanes_p) {
+        for (int pos = p0 + pl; pos < p1; pos += lanes_p) {
             float v[8];
             half8_to_float(ldg16(base + (size_t)pos * g.C), v);
 #pragma unroll
@@ -787,16 +790,15 @@ __global__ void __launch_bounds__(256) gem_train_fwd_kernel(GemTrainParams g) {
     if (tid < g.C) {
         float s = 0.f, sl = 0.f;
         for (int l = 0; l < lanes_p; ++l) { s += s_part[0][l][tid]; sl += s_part[1][l][tid]; }
-        const float m = s / (float)g.P;
-        const size_t o = (size_t)b * g.T * g.C + (size_t)t * g.C + tid;
-        g.pooled[o] = m;
-        g.mlog[o] = sl / (float)g.P;
-        g.feat[o] = powf(m, 1.0f / pw);
+        float* o = g.partials + ((((size_t)b * g.T + t) * kGemChunks + blockIdx.z) * 2) * g.C;
+        o[tid] = s;
+        o[g.C + tid] = sl;
     }
 }
 
 struct HeadTrainParams {
-    const float *feat, *pooled, *mlog;     // [b][F]
+    const float* gem_partials;             // gem_train_fwd_kernel output
+    float *feat, *pooled, *mlog;           // [b][F]: mean^(1/p), mean of c^p, mean of c^p * ln c
     const float* dmask;                    // [b][F] dropout mask (0 or 1/(1-p)) or nullptr
     const float *w, *bias;                 // classifier [K][F], [K]
     const float* targets;                  // [b][K]
@@ -804,53 +806,93 @@ struct HeadTrainParams {
     const float* scaler;                   // [0] = loss scale
     float *logits, *loss;                  // [b][K], [1] (unscaled)
     float *dw, *dbias, *dgem_p;            // gradient slices (scaled)
-    float* coef;                           // [b][F]: d feat * mean^(1/p - 1) / P, consumed by gem_bwd_kernel
-    int b, F, K, P; float alpha, gamma;
+    float* logit_partials;                 // [b][ceil(F / 256)][K]
+    float* dp_partials;                    // [gridDim.x] partial sums of d p
+    float* coef;                           // [b][F]: d feat * mean^(1/p - 1) / (p P), consumed by gem_bwd_kernel
+    int b, F, K, P, C; float alpha, gamma;
 };
-// single CTA (b * K and F are tiny); dynamic smem: (2 * b * K + 8) floats
-__global__ void __launch_bounds__(256) head_train_kernel(HeadTrainParams h) {
-    extern __shared__ float s_head[];
+// grid (ceil(F / 256), b), thread = one pooled feature: finish GeM (pooled, mlog, feat) and reduce this CTA's share of
+// the sample's logits into logit_partials[b][gridDim.x][K]
+__global__ void __launch_bounds__(256) head_logits_kernel(HeadTrainParams h) {
     __shared__ float s_red[8];
-    float* s_logit = s_head;                 // [b][K]
-    float* s_dl = s_head + h.b * h.K;        // [b][K]
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * 256 + tid;
+    const float pw = __ldg(h.gem_p);
+    float f = 0.f;
+    if (i < h.F) {
+        const size_t o = (size_t)b * h.F + i;
+        const int tt = i / h.C, c = i - tt * h.C;
+        const float* q = h.gem_partials + (((size_t)b * (h.F / h.C) + tt) * kGemChunks * 2) * h.C + c;
+        float s = 0.f, sl = 0.f;
+#pragma unroll
+        for (int z = 0; z < kGemChunks; ++z) { s += q[(size_t)z * 2 * h.C]; sl += q[(size_t)(z * 2 + 1) * h.C]; }
+        const float m = s / (float)h.P;
+        f = powf(m, 1.0f / pw);
+        h.pooled[o] = m;
+        h.mlog[o] = sl / (float)h.P;
+        h.feat[o] = f;
+        if (h.dmask) f *= h.dmask[o];
+    }
+    for (int k = 0; k < h.K; ++k) {
+        const float a = warp_sum(i < h.F ? f * __ldg(h.w + (size_t)k * h.F + i) : 0.f);
+        if (lane == 0) s_red[warp] = a;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            h.logit_partials[((size_t)b * gridDim.x + blockIdx.x) * h.K + k] = t;
+        }
+        __syncthreads();
+    }
+}
+// grid ceil(F / 256), thread = one pooled feature: focal loss gradient (recomputed per CTA from the b * K logits),
+// d classifier, d feat -> GeM backward coefficients, partial d p.  dynamic smem: 2 * b * K floats
+__global__ void __launch_bounds__(256) head_grad_kernel(HeadTrainParams h) {
+    extern __shared__ float s_dl[];          // [b][K] d loss / d logit (scaled), then [b][K] logits
+    __shared__ float s_red[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float pw = __ldg(h.gem_p);
-    for (int o = warp; o < h.b * h.K; o += 8) {          // logits: one warp per (sample, class)
-        const int b = o / h.K, k = o - b * h.K;
-        float a = 0.f;
-        for (int i = lane; i < h.F; i += 32) {
-            const float m = h.dmask ? h.dmask[(size_t)b * h.F + i] : 1.0f;
-            a = fmaf(h.feat[(size_t)b * h.F + i] * m, __ldg(h.w + (size_t)k * h.F + i), a);
-        }
-        a = warp_sum(a);
-        if (lane == 0) s_logit[o] = a + h.bias[k];
+    const int BK = h.b * h.K;
+    const float scale = h.scaler[0] / (float)BK;
+    float* s_x = s_dl + BK;
+    for (int o = tid; o < BK; o += 256) {
+        const int bb = o / h.K, k = o - bb * h.K;
+        float x = h.bias[k];
+        for (int q = 0; q < (int)gridDim.x; ++q) x += h.logit_partials[((size_t)bb * gridDim.x + q) * h.K + k];
+        if (blockIdx.x == 0) h.logits[o] = x;
+        s_x[o] = x;
+        const float t = h.targets[o];
+        const float pr = 1.0f / (1.0f + expf(-x));
+        const float ce = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+        const float q = fminf(fmaxf(pr + t - 2.0f * pr * t, 0.f), 1.0f);          // 1 - p_t
+        const float at = h.alpha >= 0.f ? h.alpha * t + (1.0f - h.alpha) * (1.0f - t) : 1.0f;
+        const float qg = powf(q, h.gamma);
+        const float dq = q > 0.f ? h.gamma * powf(q, h.gamma - 1.0f) * (1.0f - 2.0f * t) * pr * (1.0f - pr) : 0.f;
+        s_dl[o] = at * ((pr - t) * qg + ce * dq) * scale;
     }
     __syncthreads();
-    if (tid == 0) {                                       // focal loss + d logits (mean reduction, loss scale folded in)
-        const float scale = h.scaler[0] / (float)(h.b * h.K);
-        float total = 0.f;
-        for (int o = 0; o < h.b * h.K; ++o) {
-            const float x = s_logit[o], t = h.targets[o];
-            const float pr = 1.0f / (1.0f + expf(-x));
-            const float ce = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
-            const float q = fminf(fmaxf(pr + t - 2.0f * pr * t, 0.f), 1.0f);          // 1 - p_t
-            const float at = h.alpha >= 0.f ? h.alpha * t + (1.0f - h.alpha) * (1.0f - t) : 1.0f;
-            const float qg = powf(q, h.gamma);
-            total += at * ce * qg;
-            const float dq = q > 0.f ? h.gamma * powf(q, h.gamma - 1.0f) * (1.0f - 2.0f * t) * pr * (1.0f - pr) : 0.f;
-            s_dl[o] = at * ((pr - t) * qg + ce * dq) * scale;
-            h.logits[o] = x;
+    if (blockIdx.x == 0) {
+        if (tid == 0) {                                   // loss value, fixed summation order
+            float total = 0.f;
+            for (int o = 0; o < BK; ++o) {
+                const float x = s_x[o], t = h.targets[o];
+                const float pr = 1.0f / (1.0f + expf(-x));
+                const float ce = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+                const float q = fminf(fmaxf(pr + t - 2.0f * pr * t, 0.f), 1.0f);
+                const float at = h.alpha >= 0.f ? h.alpha * t + (1.0f - h.alpha) * (1.0f - t) : 1.0f;
+                total += at * ce * powf(q, h.gamma);
+            }
+            h.loss[0] = total / (float)BK;
         }
-        h.loss[0] = total / (float)(h.b * h.K);
-    }
-    __syncthreads();
-    if (tid < h.K) {
-        float a = 0.f;
-        for (int b = 0; b < h.b; ++b) a += s_dl[b * h.K + tid];
-        h.dbias[tid] = a;
+        if (tid < h.K) {
+            float a = 0.f;
+            for (int b = 0; b < h.b; ++b) a += s_dl[b * h.K + tid];
+            h.dbias[tid] = a;
+        }
     }
     float dp_acc = 0.f;
-    for (int i = tid; i < h.F; i += 256) {
+    const int i = blockIdx.x * 256 + tid;
+    if (i < h.F) {
         for (int k = 0; k < h.K; ++k) {                   // d classifier.weight
             float a = 0.f;
             for (int b = 0; b < h.b; ++b) {
@@ -875,26 +917,34 @@ __global__ void __launch_bounds__(256) head_train_kernel(HeadTrainParams h) {
     __syncthreads();
     if (tid == 0) {
         float a = 0.f;
-        for (int i = 0; i < 8; ++i) a += s_red[i];
-        h.dgem_p[0] = a;
+        for (int w = 0; w < 8; ++w) a += s_red[w];
+        h.dp_partials[blockIdx.x] = a;
     }
 }
+__global__ void head_dp_reduce_kernel(const float* partials, int n, float* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float a = 0.f;
+    for (int i = 0; i < n; ++i) a += partials[i];
+    out[0] = a;
+}
 
-// d x[b][t][pos][c] = coef[b][t*C + c] * p * c^(p-1) for x > eps (clamp passes no gradient below eps)
+// d x[b][t][pos][c] = coef[b][t*C + c] * p * c^(p-1) for x >= eps (clamp passes no gradient below eps); grid (T, b, kGemChunks)
 struct GemBwdParams {
     const __half* x; const float* coef; const float* p; __half* dx;
     int T, P, C; float eps;
 };
 __global__ void __launch_bounds__(256) gem_bwd_kernel(GemBwdParams g) {
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    const int C8 = g.C >> 3, lanes_p = min(256 / C8, 8);
+    const int C8 = g.C >> 3, lanes_p = 256 / C8;
     const int cg = tid % C8, pl = tid / C8;
     if (pl >= lanes_p) return;
     const float pw = __ldg(g.p);
+    const int per = (g.P + kGemChunks - 1) / kGemChunks;
+    const int p0 = blockIdx.z * per, p1 = min(g.P, p0 + per);
     float cf[8];
     load8(g.coef + (size_t)b * g.T * g.C + (size_t)t * g.C, cg, cf);
     const size_t base = (((size_t)b * g.T + t) * g.P) * g.C + cg * 8;
-    for (int pos = pl; pos < g.P; pos += lanes_p) {
+    for (int pos = p0 + pl; pos < p1; pos += lanes_p) {
         float v[8], o[8];
         half8_to_float(ldg16(g.x + base + (size_t)pos * g.C), v);
 #pragma unroll
@@ -939,10 +989,16 @@ __global__ void scaler_update_kernel(float* scaler, float growth, float backoff,
     }
     scaler[2] = 0.0f;
 }
-// fp32 master weight [R][Cc] -> fp16 copy and fp16 transposed copy [Cc][R] (operands of the forward / dgrad GEMMs)
-__global__ void __launch_bounds__(256) cast_transpose_kernel(const float* src, __half* dst, __half* dst_t, int R, int Cc) {
+// fp32 master weight [R][Cc] -> fp16 copy and fp16 transposed copy [Cc][R] (operands of the forward / dgrad GEMMs);
+// blockIdx.z selects the weight from a device table so that one launch refreshes all of them
+struct CastJob { const float* src; __half* dst; __half* dst_t; int R, Cc; };
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const CastJob* jobs) {
     __shared__ float tile[32][33];
+    const CastJob j = jobs[blockIdx.z];
+    const float* src = j.src; __half* dst = j.dst; __half* dst_t = j.dst_t;
+    const int R = j.R, Cc = j.Cc;
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    if (r0 >= R || c0 >= Cc) return;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int i = ty; i < 32; i += 8) {
         const int r = r0 + i, c = c0 + tx;

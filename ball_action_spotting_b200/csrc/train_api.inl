@@ -40,6 +40,8 @@ struct MdsTrainer {
     size_t n_params = 0, n_stats = 0;
     float *P = nullptr, *G = nullptr, *Mom = nullptr, *S = nullptr, *scaler = nullptr, *bn_scratch = nullptr, *zeros = nullptr, *dw27 = nullptr;
     __half* w16 = nullptr;
+    CastJob* cast_jobs = nullptr;   // device table of the fp16 operand refreshes (one launch)
+    int n_cast = 0, cast_gx = 0, cast_gy = 0;
     __half* zeros16 = nullptr;   // [1152][64] zero bias matrix of the tcgen05 GEMMs (no conv in this path has a bias)
     TrainGemmW proj2d, proj3d;
     TrainBn bn_p2d, bn_p3d;
@@ -152,6 +154,23 @@ extern "C" int mds_train_create(const MdsTrainConfig* cfg, MdsTrainer** out) {
         b.dw27 = t->dw27 + i * 2 * 27 * (size_t)mid;
         b.dw27f = b.dw27 + 27 * (size_t)mid;
     }
+    {   // table of fp16 operand refreshes
+        std::vector<CastJob> jobs;
+        auto add = [&](const TrainGemmW& w) {
+            jobs.push_back({t->P + w.off, w.w16, w.w16t, w.N, w.K});
+            if ((w.K + 31) / 32 > t->cast_gx) t->cast_gx = (w.K + 31) / 32;
+            if ((w.N + 31) / 32 > t->cast_gy) t->cast_gy = (w.N + 31) / 32;
+        };
+        add(t->proj2d);
+        for (auto& b : t->blocks) { add(b.pw); add(b.pwl); }
+        add(t->proj3d);
+        t->n_cast = (int)jobs.size();
+        if (cudaMalloc((void**)&t->cast_jobs, jobs.size() * sizeof(CastJob)) != cudaSuccess ||
+            cudaMemcpy(t->cast_jobs, jobs.data(), jobs.size() * sizeof(CastJob), cudaMemcpyHostToDevice) != cudaSuccess) {
+            mds_train_destroy(t);
+            return fail(MDS_ERR_CUDA, "mds_train_create: cast table");
+        }
+    }
     const float init[4] = {cfg->amp ? (cfg->init_scale > 0.f ? cfg->init_scale : 65536.0f) : 1.0f, 0.f, 0.f, 0.f};
     cudaMemcpy(t->scaler, init, sizeof(init), cudaMemcpyHostToDevice);
     *out = t;
@@ -162,7 +181,7 @@ extern "C" int mds_train_destroy(MdsTrainer* t) {
     if (!t) return MDS_OK;
     DeviceGuard g(t->cfg.device);
     cudaFree(t->P); cudaFree(t->G); cudaFree(t->Mom); cudaFree(t->S); cudaFree(t->scaler); cudaFree(t->bn_scratch);
-    cudaFree(t->zeros); cudaFree(t->w16); cudaFree(t->dw27); cudaFree(t->zeros16);
+    cudaFree(t->zeros); cudaFree(t->w16); cudaFree(t->dw27); cudaFree(t->zeros16); cudaFree(t->cast_jobs);
     delete t;
     return MDS_OK;
 }
@@ -230,20 +249,13 @@ extern "C" int mds_train_scaler_state(MdsTrainer* t, float* host4) {
 }
 
 static int train_derive(MdsTrainer* t, cudaStream_t st) {
-    auto cast = [&](const TrainGemmW& w) -> int {
-        dim3 grid((w.K + 31) / 32, (w.N + 31) / 32);
-        cast_transpose_kernel<<<grid, 256, 0, st>>>(t->P + w.off, w.w16, w.w16t, w.N, w.K);
-        LAUNCH_CHECK("cast_transpose");
-        return MDS_OK;
-    };
     ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
-    TRY(cast(t->proj2d));
+    cast_transpose_kernel<<<dim3(t->cast_gx, t->cast_gy, t->n_cast), 256, 0, st>>>(t->cast_jobs);
+    LAUNCH_CHECK("cast_transpose");
     for (auto& b : t->blocks) {
-        TRY(cast(b.pw)); TRY(cast(b.pwl));
         dw3_weights_kernel<<<(27 * t->mid() + 255) / 256, 256, 0, st>>>(t->P + b.dw, b.dw27, b.dw27f, t->mid());
         LAUNCH_CHECK("dw3_weights");
     }
-    TRY(cast(t->proj3d));
     return MDS_OK;
 }
 
@@ -268,16 +280,25 @@ static int train_gemm(MdsTrainer* t, const __half* A, const __half* W, const __h
     return launch_gemm(A, W, t->zeros, res, nullptr, C, M, 1, N, K, 0, st);
 }
 
-constexpr int kTrainChunkRows = 128;
-static int train_chunks(int rows_per_sample) { return (rows_per_sample + kTrainChunkRows - 1) / kTrainChunkRows; }
+// rows per CTA of the column kernels: about four CTAs per SM in total, so that the grid is whole waves at 2 CTAs / SM
+static int train_chunk_rows(int rows_per_sample, int b) {
+    int per_sample = (4 * num_sms()) / (b > 0 ? b : 1);
+    if (per_sample < 1) per_sample = 1;
+    int rows = (rows_per_sample + per_sample - 1) / per_sample;
+    return rows < 16 ? 16 : rows;
+}
+static int train_chunks(int rows_per_sample, int b) {
+    const int r = train_chunk_rows(rows_per_sample, b);
+    return (rows_per_sample + r - 1) / r;
+}
 
-static EwParams ew_base(const __half* y, int C, int rows_per_sample) {
+static EwParams ew_base(const __half* y, int C, int rows_per_sample, int b) {
     EwParams p;
     memset(&p, 0, sizeof(p));
-    p.y = y; p.C = C; p.rows_per_sample = rows_per_sample; p.rows_per_chunk = kTrainChunkRows;
+    p.y = y; p.C = C; p.rows_per_sample = rows_per_sample; p.rows_per_chunk = train_chunk_rows(rows_per_sample, b);
     return p;
 }
-static dim3 ew_grid(int rows_per_sample, int b) { return dim3(train_chunks(rows_per_sample), b); }
+static dim3 ew_grid(int rows_per_sample, int b) { return dim3(train_chunks(rows_per_sample, b), b); }
 
 // batch statistics partials -> scale / shift (+ running-stat update).  `ref` = the per-channel shift the partial sums
 // were taken against (the running mean *before* this update: a cheap, data-independent guess of the batch mean that
@@ -290,7 +311,7 @@ static int train_bn_finalize(MdsTrainer* t, const TrainBn& bn, const float* part
     f.running_mean = t->S + bn.rm; f.running_var = t->S + bn.rv;
     f.scale = bn.scale(); f.shift = bn.shift(); f.mean = bn.mean(); f.rstd = bn.rstd();
     f.C = bn.C; f.count = (float)count; f.eps = 1e-5f; f.momentum = 0.1f;
-    bn_fwd_finalize_kernel<<<(bn.C + 31) / 32, 256, 0, st>>>(f);
+    bn_fwd_finalize_kernel<<<(bn.C + kFinCh - 1) / kFinCh, kFinThreads, 0, st>>>(f);
     LAUNCH_CHECK("bn_fwd_finalize");
     return MDS_OK;
 }
@@ -298,19 +319,19 @@ static int train_bn_finalize(MdsTrainer* t, const TrainBn& bn, const float* part
 static int train_bn_stats(MdsTrainer* t, const TrainBn& bn, const __half* y, int b, int rows_per_sample, float* partials, cudaStream_t st) {
     {
         ProfScope ps(MDS_KIND_TRAIN_BN, st);
-        EwParams p = ew_base(y, bn.C, rows_per_sample);
+        EwParams p = ew_base(y, bn.C, rows_per_sample, b);
         p.partials = partials; p.mean = t->S + bn.rm;
         bn_stats_kernel<<<ew_grid(rows_per_sample, b), kEwThreads, 0, st>>>(p);
         LAUNCH_CHECK("bn_stats");
     }
-    return train_bn_finalize(t, bn, partials, train_chunks(rows_per_sample) * b, (double)b * rows_per_sample, t->S + bn.rm, st);
+    return train_bn_finalize(t, bn, partials, train_chunks(rows_per_sample, b) * b, (double)b * rows_per_sample, t->S + bn.rm, st);
 }
 
 template <int MODE>
 static int train_bn_fwd(const TrainBn& bn, const __half* y, const __half* res, __half* out, float* partials, const float* smul,
                         const float* bmul, int b, int rows_per_sample, cudaStream_t st) {
     ProfScope ps(MDS_KIND_TRAIN_BN, st);
-    EwParams p = ew_base(y, bn.C, rows_per_sample);
+    EwParams p = ew_base(y, bn.C, rows_per_sample, b);
     p.g = res; p.out = out; p.partials = partials; p.scale = bn.scale(); p.shift = bn.shift(); p.smul = smul; p.bmul = bmul;
     bn_fwd_kernel<MODE><<<ew_grid(rows_per_sample, b), kEwThreads, 0, st>>>(p);
     LAUNCH_CHECK("bn_fwd");
@@ -321,7 +342,7 @@ static int train_bn_fwd(const TrainBn& bn, const __half* y, const __half* res, _
 static int train_bn_bwd(MdsTrainer* t, const TrainBn& bn, bool act, const __half* y, const __half* g, __half* dy, const float* smul,
                         const float* sadd, const float* bmul, int b, int rows_per_sample, float* partials, cudaStream_t st) {
     ProfScope ps(MDS_KIND_TRAIN_BN, st);
-    EwParams p = ew_base(y, bn.C, rows_per_sample);
+    EwParams p = ew_base(y, bn.C, rows_per_sample, b);
     p.g = g; p.out = dy; p.partials = partials; p.scale = bn.scale(); p.shift = bn.shift(); p.mean = bn.mean(); p.rstd = bn.rstd();
     p.smul = smul; p.sadd = sadd; p.bmul = bmul; p.c1 = bn.c1(); p.c2 = bn.c2(); p.gr = bn.gr();
     const dim3 grid = ew_grid(rows_per_sample, b);
@@ -332,7 +353,7 @@ static int train_bn_bwd(MdsTrainer* t, const TrainBn& bn, bool act, const __half
     f.partials = partials; f.nparts = grid.x * b; f.gamma = t->P + bn.gamma; f.rstd = bn.rstd();
     f.dgamma = t->G + bn.gamma; f.dbeta = t->G + bn.beta; f.c1 = bn.c1(); f.c2 = bn.c2(); f.gr = bn.gr();
     f.C = bn.C; f.count = (float)((double)b * rows_per_sample);
-    bn_bwd_finalize_kernel<<<(bn.C + 31) / 32, 256, 0, st>>>(f);
+    bn_bwd_finalize_kernel<<<(bn.C + kFinCh - 1) / kFinCh, kFinThreads, 0, st>>>(f);
     LAUNCH_CHECK("bn_bwd_finalize");
     if (act) bn_bwd_apply_kernel<true><<<grid, kEwThreads, 0, st>>>(p);
     else bn_bwd_apply_kernel<false><<<grid, kEwThreads, 0, st>>>(p);
@@ -389,6 +410,7 @@ static int train_dw3_conv(const __half* in, __half* out, const float* w27, const
     p.rows_per_chunk = (H + chunks - 1) / chunks;
     p.chunks = (H + p.rows_per_chunk - 1) / p.rows_per_chunk;
     p.nparts = p.chunks * T * p.xtiles;
+    if (p.nparts > kDwMaxParts * 4) return fail(MDS_ERR_INVALID, "dw3 (train): %d statistics partials per sample exceed %d", p.nparts, kDwMaxParts * 4);
     if (nparts_total) *nparts_total = p.nparts * b;
     using Cfg = DwCfg<3, 1>;
     auto kern = dwconv_kernel<3, 1, true>;
@@ -441,7 +463,7 @@ struct TrainWs {
     __half *y0, *yp, *ap, *dP, *dP2, *dXa, *dXb, *D3, *DM1, *DM2;
     std::vector<__half*> x, y1, a1, y2, a2g, y3;
     float *partials, *wpart, *dwpart, *se_s, *se_h, *se_g, *se_dg, *se_dh, *se_sadd, *dp_mask, *do_mask;
-    float *feat, *pooled, *mlog, *coef;
+    float *feat, *pooled, *mlog, *coef, *gem_part, *dp_part, *se_sum, *logit_part;
 };
 static int train_ws_take(const MdsTrainer* t, int b, int fh, int fw, Arena& ar, TrainWs& w) {
     const int P = fh * fw;
@@ -462,7 +484,12 @@ static int train_ws_take(const MdsTrainer* t, int b, int fh, int fw, Arena& ar, 
     w.dP = ar.take<__half>(M * pj); w.dP2 = ar.take<__half>(M * pj);
     w.dXa = ar.take<__half>(M * c3); w.dXb = ar.take<__half>(M * c3); w.D3 = ar.take<__half>(M * c3);
     w.DM1 = ar.take<__half>(M * mid); w.DM2 = ar.take<__half>(M * mid);
-    w.partials = ar.take<float>((size_t)b * train_chunks(T * P) * 2 * cmax);
+    size_t npart = (size_t)b * train_chunks(T * P, b);
+    {   // the depthwise kernel's fused statistics use its own CTA count
+        const size_t dwp = (size_t)b * kDwMaxParts * 4;
+        if (dwp > npart) npart = dwp;
+    }
+    w.partials = ar.take<float>(npart * 2 * cmax);
     size_t wp = 0;
     auto upd = [&](int N, int K) { size_t f = wgrad_partial_floats((long long)M, N, K, nullptr, nullptr); if (f > wp) wp = f; };
     upd(c3, 192); upd(mid, c3); upd(c3, mid); upd(pj, c3);
@@ -473,6 +500,9 @@ static int train_ws_take(const MdsTrainer* t, int b, int fh, int fw, Arena& ar, 
     w.dp_mask = ar.take<float>((size_t)(nb > 0 ? nb : 1) * b); w.do_mask = ar.take<float>((size_t)b * t->F());
     w.feat = ar.take<float>((size_t)b * t->F()); w.pooled = ar.take<float>((size_t)b * t->F());
     w.mlog = ar.take<float>((size_t)b * t->F()); w.coef = ar.take<float>((size_t)b * t->F());
+    w.gem_part = ar.take<float>((size_t)b * t->F() * kGemChunks * 2); w.dp_part = ar.take<float>((size_t)(t->F() + 255) / 256);
+    w.se_sum = ar.take<float>((size_t)b * mid);
+    w.logit_part = ar.take<float>((size_t)b * ((t->F() + 255) / 256) * t->cfg.num_classes);
     return ar.overflow ? 1 : 0;
 }
 
@@ -537,11 +567,13 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
         TRY(train_bn_fwd<1>(B.bn2, w.y2[i], nullptr, nullptr, w.partials, nullptr, nullptr, b, rows, st));   // SE squeeze sums
         {
             ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
+            colsum_finalize_kernel<<<dim3((mid + kFinCh - 1) / kFinCh, b), kFinThreads, 0, st>>>(w.partials, train_chunks(rows, b), mid, inv_rows, se_s);
+            LAUNCH_CHECK("colsum_finalize");
             SeTrainParams sp;
             memset(&sp, 0, sizeof(sp));
-            sp.partials = w.partials; sp.nparts = train_chunks(rows);
+            sp.sums = se_s;
             sp.w1 = t->P + B.se_w1; sp.b1 = t->P + B.se_b1; sp.w2 = t->P + B.se_w2; sp.b2 = t->P + B.se_b2;
-            sp.s = se_s; sp.hpre = se_h; sp.gate = se_g; sp.C = mid; sp.rd = rd; sp.inv_count = inv_rows;
+            sp.hpre = se_h; sp.gate = se_g; sp.C = mid; sp.rd = rd; sp.inv_count = inv_rows;
             se_train_fwd_kernel<<<b, 256, se_smem, st>>>(sp);
             LAUNCH_CHECK("se_train_fwd");
         }
@@ -558,22 +590,29 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
     {
         ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
         GemTrainParams gp;
-        gp.x = w.ap; gp.p = t->P + t->gem_p; gp.feat = w.feat; gp.pooled = w.pooled; gp.mlog = w.mlog; gp.T = T; gp.P = P; gp.C = pj; gp.eps = 1e-6f;
-        gem_train_fwd_kernel<<<dim3(T, b), 256, 0, st>>>(gp);
+        gp.x = w.ap; gp.p = t->P + t->gem_p; gp.partials = w.gem_part; gp.T = T; gp.P = P; gp.C = pj; gp.eps = 1e-6f;
+        gem_train_fwd_kernel<<<dim3(T, b, kGemChunks), 256, 0, st>>>(gp);
         LAUNCH_CHECK("gem_train_fwd");
         HeadTrainParams hp;
-        hp.feat = w.feat; hp.pooled = w.pooled; hp.mlog = w.mlog; hp.dmask = do_mask; hp.w = t->P + t->cls_w; hp.bias = t->P + t->cls_b;
+        hp.gem_partials = w.gem_part; hp.feat = w.feat; hp.pooled = w.pooled; hp.mlog = w.mlog; hp.dmask = do_mask;
+        hp.w = t->P + t->cls_w; hp.bias = t->P + t->cls_b;
         hp.targets = a->targets; hp.gem_p = t->P + t->gem_p; hp.scaler = t->scaler;
         hp.logits = a->logits_out ? a->logits_out : w.se_dg;      // scratch when the caller does not want them
         hp.loss = a->loss_out ? a->loss_out : w.se_dh;
-        hp.dw = t->G + t->cls_w; hp.dbias = t->G + t->cls_b; hp.dgem_p = t->G + t->gem_p; hp.coef = w.coef;
-        hp.b = b; hp.F = F; hp.K = K; hp.P = P; hp.alpha = t->cfg.focal_alpha; hp.gamma = t->cfg.focal_gamma;
-        head_train_kernel<<<1, 256, (size_t)(2 * b * K + 8) * sizeof(float), st>>>(hp);
-        LAUNCH_CHECK("head_train");
+        hp.dw = t->G + t->cls_w; hp.dbias = t->G + t->cls_b; hp.dgem_p = t->G + t->gem_p; hp.dp_partials = w.dp_part; hp.coef = w.coef;
+        hp.b = b; hp.F = F; hp.K = K; hp.P = P; hp.C = pj; hp.alpha = t->cfg.focal_alpha; hp.gamma = t->cfg.focal_gamma;
+        const int hblocks = (F + 255) / 256;
+        hp.logit_partials = w.logit_part;
+        head_logits_kernel<<<dim3(hblocks, b), 256, 0, st>>>(hp);
+        LAUNCH_CHECK("head_logits");
+        head_grad_kernel<<<hblocks, 256, (size_t)2 * b * K * sizeof(float), st>>>(hp);
+        LAUNCH_CHECK("head_grad");
+        head_dp_reduce_kernel<<<1, 32, 0, st>>>(w.dp_part, hblocks, t->G + t->gem_p);
+        LAUNCH_CHECK("head_dp_reduce");
         // ============================================= backward =============================================
         GemBwdParams gb;
         gb.x = w.ap; gb.coef = w.coef; gb.p = t->P + t->gem_p; gb.dx = w.dP; gb.T = T; gb.P = P; gb.C = pj; gb.eps = 1e-6f;
-        gem_bwd_kernel<<<dim3(T, b), 256, 0, st>>>(gb);
+        gem_bwd_kernel<<<dim3(T, b, kGemChunks), 256, 0, st>>>(gb);
         LAUNCH_CHECK("gem_bwd");
     }
     g_prof_tag = 450;
@@ -592,18 +631,20 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
         TRY(train_gemm(t, w.D3, B.pwl.w16t, nullptr, w.DM1, M, mid, c3, st));         // d (a2 * gate)
         {   // SE backward: d gate -> d squeeze, parameter gradients
             ProfScope ps(MDS_KIND_TRAIN_BN, st);
-            EwParams p = ew_base(w.y2[i], mid, rows);
+            EwParams p = ew_base(w.y2[i], mid, rows, b);
             p.g = w.DM1; p.partials = w.partials; p.scale = B.bn2.scale(); p.shift = B.bn2.shift();
             dgate_kernel<<<ew_grid(rows, b), kEwThreads, 0, st>>>(p);
             LAUNCH_CHECK("dgate");
         }
         {
             ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
+            colsum_finalize_kernel<<<dim3((mid + kFinCh - 1) / kFinCh, b), kFinThreads, 0, st>>>(w.partials, train_chunks(rows, b), mid, 1.0f, w.se_sum);
+            LAUNCH_CHECK("colsum_finalize");
             SeTrainParams sp;
             memset(&sp, 0, sizeof(sp));
-            sp.partials = w.partials; sp.nparts = train_chunks(rows);
+            sp.sums = w.se_sum;
             sp.w1 = t->P + B.se_w1; sp.b1 = t->P + B.se_b1; sp.w2 = t->P + B.se_w2; sp.b2 = t->P + B.se_b2;
-            sp.s = se_s; sp.hpre = se_h; sp.gate = se_g; sp.dgpre = w.se_dg; sp.dhpre = w.se_dh; sp.sadd = w.se_sadd;
+            sp.hpre = se_h; sp.gate = se_g; sp.dgpre = w.se_dg; sp.dhpre = w.se_dh; sp.sadd = w.se_sadd;
             sp.C = mid; sp.rd = rd; sp.inv_count = inv_rows;
             se_train_bwd_kernel<<<b, 256, se_smem, st>>>(sp);
             LAUNCH_CHECK("se_train_bwd");
