@@ -52,6 +52,8 @@ SIGNATURES = {
     "mds_forward": (_i, [_vp, _FP, _i, _vp, _i, _vp, _sz, _vp]),
     "mds_nchw32_to_nhwc16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mds_nhwc16_to_nchw32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mds_gather_stacks": (_i, [_vp, _vp, C.c_longlong, _i, _i, _i, C.c_longlong, _vp]),
+    "mds_axpby": (_i, [_vp, _vp, _f, _f, C.c_longlong, _vp]),
     "mds_k_stem": (_i, [_FP, _i, _vp, _vp, _vp, _vp]),
     "mds_k_conv3x3": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mds_k_gemm1x1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -71,6 +73,8 @@ SIGNATURES = {
     "mds_train_step": (_i, [_vp, C.POINTER(MdsTrainStepArgs), _vp, _sz, _vp]),
     "mds_train_scaler_state": (_i, [_vp, _vp]),
     "mds_train_batches_tracked": (C.c_longlong, [_vp]),
+    "mds_post_processing_workspace_bytes": (_sz, [_i, _i]),
+    "mds_post_processing": (_i, [_vp, _i, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mds_launch_count": (C.c_longlong, [_i]),
     "mds_profile_begin": (_i, []),
     "mds_profile_end": (_i, [_vp, _vp, _vp, _i, _vp]),

@@ -21,6 +21,7 @@
 #include "se_head.cuh"
 #include "stem.cuh"
 #include "train.cuh"
+#include "postproc.cuh"
 
 using namespace mds;
 
@@ -906,6 +907,25 @@ extern "C" int mds_nhwc16_to_nchw32(const void* src, float* dst, int n, int C, i
     return MDS_OK;
 }
 
+extern "C" int mds_gather_stacks(const void* feats, void* out, long long first_image, int hop, int n_pred, int T, long long plane_elems,
+                                 void* stream) {
+    if (!feats || !out) return fail(MDS_ERR_INVALID, "gather_stacks: null argument");
+    if (n_pred <= 0 || T <= 0) return MDS_OK;
+    if (plane_elems <= 0 || plane_elems % 8 || first_image < 0 || hop < 0 || n_pred > 65535)
+        return fail(MDS_ERR_INVALID, "gather_stacks: plane must be a multiple of 8 fp16 elements, n_pred <= 65535");
+    gather_stacks_kernel<<<dim3(T, n_pred), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint4*>(feats), reinterpret_cast<uint4*>(out), first_image, hop, T, plane_elems / 8);
+    LAUNCH_CHECK("gather_stacks");
+    return MDS_OK;
+}
+extern "C" int mds_axpby(float* y, const float* x, float a, float b, long long n, void* stream) {
+    if (!y || !x) return fail(MDS_ERR_INVALID, "axpby: null argument");
+    if (n <= 0) return MDS_OK;
+    axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, x, a, b, n);
+    LAUNCH_CHECK("axpby");
+    return MDS_OK;
+}
+
 extern "C" int mds_k_stem(const MdsFrames* frames, int n_images, const void* wh, const float* bias, void* out, void* stream) {
     if (!frames) return fail(MDS_ERR_INVALID, "null frames");
     return launch_stem(*frames, n_images, reinterpret_cast<const __half*>(wh), bias, reinterpret_cast<__half*>(out),
@@ -949,3 +969,4 @@ extern "C" int mds_k_linear(const float* feat, const float* w, const float* bias
 }
 
 #include "train_api.inl"
+#include "postproc_api.inl"

@@ -194,6 +194,22 @@ __global__ void __launch_bounds__(256) linear_head_kernel(const float* feat, con
     }
 }
 
+// ---- sliding-window assembly (src/predictors.py:66-68: torch.cat of the cached per-triple features) ------------------
+// out[p][t] = feats[first + p + hop * t]: window p stacks the cached encoder features of T triples `hop` frames apart.
+// grid (T, n_pred); plane_vec = 16-byte vectors per (h, w, C) feature plane
+__global__ void __launch_bounds__(256) gather_stacks_kernel(const uint4* feats, uint4* out, long long first, int hop, int T,
+                                                            long long plane_vec) {
+    const int t = blockIdx.x, pidx = blockIdx.y;
+    const uint4* src = feats + (first + pidx + (long long)hop * t) * plane_vec;
+    uint4* dst = out + ((long long)pidx * T + t) * plane_vec;
+    for (long long i = threadIdx.x; i < plane_vec; i += 256) dst[i] = __ldg(src + i);
+}
+// y = a * y + b * x (mean of the TTA branches, predictors.py:72)
+__global__ void __launch_bounds__(256) axpby_kernel(float* y, const float* x, float a, float b, long long n) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) y[i] = a * y[i] + b * x[i];
+}
+
 // ---- boundary layout converters (the reference API is NCHW float32; the engine is NHWC fp16) ----------------
 // src [n][C][P] f32 -> dst [n][P][C] f16
 __global__ void __launch_bounds__(256) nchw32_to_nhwc16_kernel(const float* src, __half* dst, int C, int P) {

@@ -174,6 +174,24 @@ class Engine:
         check(self.lib.mds_nhwc16_to_nchw32(x.data_ptr(), out.data_ptr(), n, c, P, _stream(self.device)), "nhwc16_to_nchw32")
         return out
 
+    def gather_stacks(self, feats: torch.Tensor, first_image: int, hop: int, n_pred: int, T: int) -> torch.Tensor:
+        """feats fp16 (n_img, fh, fw, C) -> (n_pred, T, fh, fw, C): window p = images first_image + p + hop * t."""
+        n_img = feats.shape[0]
+        if first_image < 0 or first_image + (n_pred - 1) + hop * (T - 1) >= n_img:
+            raise RuntimeError("gather_stacks: window reaches outside the cached features")
+        plane = feats[0].numel()
+        out = torch.empty((n_pred, T, *feats.shape[1:]), dtype=feats.dtype, device=self.device)
+        for p0 in range(0, n_pred, 32768):
+            n = min(32768, n_pred - p0)
+            check(self.lib.mds_gather_stacks(feats.data_ptr(), out[p0:].data_ptr(), first_image + p0, hop, n, T, plane,
+                                             _stream(self.device)), "mds_gather_stacks")
+        return out
+
+    def axpby_(self, y: torch.Tensor, x: torch.Tensor, a: float, b: float) -> torch.Tensor:
+        """y <- a * y + b * x (float32, in place)."""
+        check(self.lib.mds_axpby(y.data_ptr(), x.data_ptr(), float(a), float(b), y.numel(), _stream(self.device)), "mds_axpby")
+        return y
+
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.mds_launch_count(1 if reset else 0))
 

@@ -115,6 +115,9 @@ class MultiDimStackerPredictor:
             eng = self.model.nn_module.engine(self.device)
             x = eng.forward_3d(feats.contiguous())
             prediction = eng.forward_head(x, sigmoid=True)                 # prediction_transform fused
-            prediction = torch.mean(prediction, dim=0)
+            if prediction.shape[0] == 2:                                   # TTA: mean of the two branches (predictors.py:72)
+                prediction = eng.axpby_(prediction[0], prediction[1], 0.5, 0.5)
+            else:
+                prediction = prediction[0]
             return prediction, predict_index
         return None, predict_index

@@ -95,14 +95,14 @@ class SlidingSweep:
                 desc = eng.frames_desc(frames, H, W, h * w, self.step * h * w, hflip=flip,
                                        offset_elems=(s_lo - first_frame) * h * w)
                 feats.append(eng.forward_2d(desc, n_img))      # (n_img, fh, fw, 192)
-            idx = (torch.arange(c0, c1, device=frames.device)[:, None] - self.gen.behind - s_lo
-                   + hop * torch.arange(self.T, device=frames.device)[None, :])            # (n_pred, T)
             probs = None
-            for f in feats:
-                x = f[idx.reshape(-1)].view(c1 - c0, self.T, *f.shape[1:])                 # (n_pred, T, fh, fw, 192)
-                pr = eng.forward_head(eng.forward_3d(x.contiguous()), sigmoid=True)
-                probs = pr if probs is None else probs + pr
-            out.append(probs / len(feats))
+            for f in feats:     # window p = cached features of the triples starting at p - behind + hop * t (predictors.py:58-68)
+                x = eng.gather_stacks(f, c0 - self.gen.behind - s_lo, hop, c1 - c0, self.T)    # (n_pred, T, fh, fw, 192)
+                pr = eng.forward_head(eng.forward_3d(x), sigmoid=True)
+                probs = pr if probs is None else eng.axpby_(probs, pr, 1.0, 1.0)
+            if len(feats) > 1:
+                eng.axpby_(probs, probs, 1.0 / len(feats), 0.0)                               # mean over the TTA branches (:72)
+            out.append(probs)
         return torch.cat(out, 0)
 
 

@@ -93,6 +93,14 @@ int mds_forward_head(MdsHandle* h, const void* x, int b, int P, float* logits, i
 int mds_forward(MdsHandle* h, const MdsFrames* frames, int b, float* logits, int apply_sigmoid,
                 void* ws, size_t ws_bytes, void* stream);
 
+/* Sliding-window assembly (src/predictors.py:66-68: torch.cat of the per-triple cached features): window p of n_pred
+ * consecutive predictions stacks images first_image + p + hop * t, t = 0..T-1, of a cached fp16 feature buffer
+ * [n_img][plane_elems] into out [n_pred][T][plane_elems]. */
+int mds_gather_stacks(const void* feats, void* out, long long first_image, int hop, int n_pred, int T, long long plane_elems,
+                      void* stream);
+/* y = a * y + b * x over n floats: the mean over the TTA branches (predictors.py:72). */
+int mds_axpby(float* y, const float* x, float a, float b, long long n, void* stream);
+
 /* Boundary layout converters (reference tensors are NCHW float32, the engine is NHWC fp16). */
 int mds_nchw32_to_nhwc16(const float* src, void* dst, int n, int C, int P, void* stream);
 int mds_nhwc16_to_nchw32(const void* src, float* dst, int n, int C, int P, void* stream);
@@ -178,6 +186,17 @@ int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* args, void* ws, size_t
 /* host4: loss scale, growth tracker, found_inf flag, optimizer steps performed; synchronises the device */
 int mds_train_scaler_state(MdsTrainer* t, float* host4);
 long long mds_train_batches_tracked(const MdsTrainer* t);   /* BatchNorm num_batches_tracked increment */
+
+/* ---- post-processing of raw predictions into action spots ----------------------------------------------------------
+ * Replaces post_processing (src/utils.py:55-64) for every class at once: scipy.ndimage.gaussian_filter (1-D, 'reflect',
+ * weights = scipy's _gaussian_kernel1d(sigma, 0, radius) passed in by the host, radius = int(4 * sigma + 0.5)) followed by
+ * scipy.signal.find_peaks(height=height, distance=distance).  raw: device f32 [n_frames][num_classes]
+ * (`raw_predictions`, scripts/ball_action/predict.py:50-55).  Outputs (device): out_index / out_conf [num_classes][n_frames]
+ * hold, per class, the ascending peak positions (add frame_indexes[0], utils.py:63) and the smoothed value there;
+ * out_count [num_classes].  One launch, no host synchronisation. */
+size_t mds_post_processing_workspace_bytes(int n_frames, int num_classes);
+int mds_post_processing(const float* raw, int n_frames, int num_classes, const double* weights_host, int radius, float height,
+                        int distance, int* out_index, float* out_conf, int* out_count, void* ws, size_t ws_bytes, void* stream);
 
 /* number of kernels launched by this library in the calling thread since the last reset (bench "gpu_launches") */
 long long mds_launch_count(int reset);
