@@ -75,6 +75,7 @@ SIGNATURES = {
     "mds_train_batches_tracked": (C.c_longlong, [_vp]),
     "mds_post_processing_workspace_bytes": (_sz, [_i, _i]),
     "mds_post_processing": (_i, [_vp, _i, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mds_set_pdl": (_i, [_i]),
     "mds_launch_count": (C.c_longlong, [_i]),
     "mds_profile_begin": (_i, []),
     "mds_profile_end": (_i, [_vp, _vp, _vp, _i, _vp]),

@@ -63,6 +63,14 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Programmatic dependent launch (PDL).  Every kernel of the forward chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: it calls pdl_trigger() first thing (the next kernel's CTAs may be
+// scheduled onto SMs as this grid drains) and pdl_wait() before it touches anything a previous kernel wrote or still
+// reads (griddepcontrol.wait returns once every prerequisite grid has completed and its memory is visible).  Only
+// weight / constant loads and on-chip set-up sit above the wait.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

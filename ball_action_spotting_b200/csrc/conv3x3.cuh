@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256 / MT, MINB) conv3x3_kernel(Conv3Params p) 
     float* s_b1 = reinterpret_cast<float*>(s_tile + 2 * Cfg::TILE);
     float* s_b2 = s_b1 + CMID;
 
+    pdl_trigger();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_x = (p.Wo + Cfg::TW - 1) / Cfg::TW, tiles_y = (p.Ho + Cfg::TH - 1) / Cfg::TH;
     const int tiles_per_img = tiles_x * tiles_y;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(256 / MT, MINB) conv3x3_kernel(Conv3Params p) 
         }
     };
 
+    pdl_wait();       // weights above are constants; activations below come from the previous kernel
     int t = blockIdx.x;
     if (t < ntiles) load_tile(t, s_tile);
     cp_async_commit();

@@ -71,6 +71,7 @@ template <int CIN, int CMID, int COUT>
 __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmIn, Conv3TcParams p) {
     using Cfg = Conv3TcCfg<CIN, CMID, COUT>;
     extern __shared__ unsigned char c3tc_smem_raw[];
+    pdl_trigger();
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c3tc_smem_raw) + 127) & ~uintptr_t(127));
     unsigned char* s_tile = smem;                                   // [2][TILE_ALLOC]
     unsigned char* s_w1 = s_tile + 2 * Cfg::TILE_ALLOC;             // [9][CIN/8][CMID][16 B]
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv3x3_tc_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    pdl_wait();       // on-chip set-up done; activations (and the output buffer) belong to earlier kernels until now
 
     auto tile_geom = [&](int tile, int& n, int& y0, int& x0, int& nm) {
         n = tile / tiles_per_img;

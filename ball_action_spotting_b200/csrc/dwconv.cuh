@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     __half* s_ring = reinterpret_cast<__half*>(dw_smem);
     float* s_part = reinterpret_cast<float*>(dw_smem + (size_t)Cfg::NST * Cfg::STAGE_HALVES * 2);   // [8][64]
 
+    pdl_trigger();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int xt = blockIdx.x % p.xtiles, slab = blockIdx.x / p.xtiles;
     const int t = blockIdx.y / p.chunks, chunk = blockIdx.y - t * p.chunks;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(DwParams p) {
     for (int i = 0; i < KT * 9; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)i * p.C + c_ld));
     const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + c_ld));
 
+    pdl_wait();       // weights above are constants; the input rows below come from the previous kernel
     const int NSTG = (NR + Cfg::RPS - 1) / Cfg::RPS;     // stages to stream (rows past NR are loaded but unused)
 #pragma unroll
     for (int j = 0; j < Cfg::NST - 1; ++j) {

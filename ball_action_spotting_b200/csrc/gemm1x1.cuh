@@ -43,6 +43,8 @@ __global__ void __launch_bounds__(256, 2) gemm1x1_kernel(GemmParams p) {
     __half* s_pipe = reinterpret_cast<__half*>(smem_raw);
     __half* s_gate = reinterpret_cast<__half*>(smem_raw + (Cfg::PIPE_BYTES > Cfg::EPI_BYTES ? Cfg::PIPE_BYTES : Cfg::EPI_BYTES));
 
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp & 3, wn = warp >> 2;
     const int tiles_per_img = (p.rows_per_img + kGemmBM - 1) / kGemmBM;

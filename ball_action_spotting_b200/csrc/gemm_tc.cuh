@@ -154,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* acc_empty = bars + 14;          // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + kTcBK - 1) / kTcBK;
 
@@ -182,6 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    pdl_wait();       // barriers, ones tile and TMEM are set up; every global access below depends on earlier kernels
 
     if (warp == 0) {
         // ================= TMA producer =================

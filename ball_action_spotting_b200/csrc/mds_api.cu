@@ -103,6 +103,22 @@ extern "C" int mds_profile_end(int* kinds, int* tags, float* ms, int capacity, i
     return MDS_OK;
 }
 
+// Launch with programmatic stream serialization (see pdl_trigger / pdl_wait in common.cuh)
+static bool g_pdl = !(getenv("MDS_PDL") && getenv("MDS_PDL")[0] == '0');     // MDS_PDL=0: plain stream serialization
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+extern "C" int mds_set_pdl(int enabled) { g_pdl = enabled != 0; return MDS_OK; }
+
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -141,8 +157,8 @@ static int launch_stem(const MdsFrames& f, int n, const __half* wh, const float*
     p.wh = wh; p.bias = bias; p.out = out;
     dim3 grid((f.W / 2 + kStemTW - 1) / kStemTW, (f.H / 2 + kStemTH - 1) / kStemTH, n);
     ProfScope ps(MDS_KIND_STEM, st);
-    if (f.dtype == 0) stem_kernel<uint8_t><<<grid, 256, 0, st>>>(p);
-    else if (f.dtype == 1) stem_kernel<float><<<grid, 256, 0, st>>>(p);
+    if (f.dtype == 0) launch_pdl(stem_kernel<uint8_t>, grid, dim3(256), 0, st, p);
+    else if (f.dtype == 1) launch_pdl(stem_kernel<float>, grid, dim3(256), 0, st, p);
     else return fail(MDS_ERR_INVALID, "stem: dtype must be 0 (uint8) or 1 (float32)");
     LAUNCH_CHECK("stem");
     return MDS_OK;
@@ -162,7 +178,7 @@ static int launch_conv3_t(const Conv3Params& p, cudaStream_t st) {
     int grid = num_sms() * MINB;
     if (grid > tiles) grid = tiles;
     ProfScope ps(MDS_KIND_CONV3X3, st);
-    kern<<<grid, 256 / MT, Cfg::SMEM, st>>>(p);
+    launch_pdl(kern, dim3(grid), dim3(256 / MT), Cfg::SMEM, st, p);
     LAUNCH_CHECK("conv3x3");
     return MDS_OK;
 }
@@ -198,7 +214,7 @@ static int launch_conv3_tc(const __half* in, __half* out, const __half* w1, cons
     int grid = num_sms();
     if (tiles < grid) grid = (int)tiles;
     ProfScope ps(MDS_KIND_CONV3X3, st);
-    kern<<<grid, kTcThreads, Cfg::SMEM, st>>>(tm, p);
+    launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::SMEM, st, tm, p);
     LAUNCH_CHECK("conv3x3_tc");
     return MDS_OK;
 }
@@ -237,7 +253,7 @@ static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
     dim3 grid((p.N + BN - 1) / BN, tiles_per_img * p.n_img);
     if (grid.y > 65535) return fail(MDS_ERR_INVALID, "gemm1x1: too many M tiles (%u)", grid.y);
     ProfScope ps(MDS_KIND_GEMM1X1, st);
-    kern<<<grid, 256, Cfg::SMEM, st>>>(p);
+    launch_pdl(kern, grid, dim3(256), Cfg::SMEM, st, p);
     LAUNCH_CHECK("gemm1x1");
     return MDS_OK;
 }
@@ -294,7 +310,7 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     int grid = num_sms();
     if (p.m_tiles < grid) grid = p.m_tiles;
     ProfScope ps(MDS_KIND_GEMM1X1, st);
-    gemm_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, tmBias, p);
+    launch_pdl(gemm_tc_kernel, dim3(grid), dim3(kTcThreads), smem, st, tmA, tmB, tmBias, p);
     LAUNCH_CHECK("gemm_tc");
     return MDS_OK;
 }
@@ -378,7 +394,7 @@ static int launch_dw_t(const DwParams& p, dim3 grid, cudaStream_t st) {
         attr_set = true;
     }
     ProfScope ps(KT == 1 ? MDS_KIND_DWCONV2D : MDS_KIND_DWCONV3D, st);
-    kern<<<grid, 256, Cfg::SMEM, st>>>(p);
+    launch_pdl(kern, grid, dim3(256), Cfg::SMEM, st, p);
     LAUNCH_CHECK("dwconv");
     return MDS_OK;
 }
@@ -431,7 +447,7 @@ static int launch_se(const float* partials, int nparts, const float* w1, const f
     const int gps = ((C >> 3) + kSeSlices - 1) / kSeSlices;
     const size_t smem = (size_t)(C + ((rd + 3) & ~3) + gps * 8) * sizeof(float);
     ProfScope ps(MDS_KIND_SE_FC, st);
-    se_fc_kernel<<<dim3(n, kSeSlices), kSeThreads, smem, st>>>(p);
+    launch_pdl(se_fc_kernel, dim3(n, kSeSlices), dim3(kSeThreads), smem, st, p);
     LAUNCH_CHECK("se_fc");
     return MDS_OK;
 }
@@ -442,7 +458,7 @@ static int launch_gem(const __half* x, float* feat, int b, int T, int P, int C, 
     GemParams g;
     g.x = x; g.feat = feat; g.T = T; g.P = P; g.C = C; g.p = pw; g.eps = eps;
     ProfScope ps(MDS_KIND_HEAD, st);
-    gem_kernel<<<dim3(T, b), 256, 0, st>>>(g);
+    launch_pdl(gem_kernel, dim3(T, b), dim3(256), 0, st, g);
     LAUNCH_CHECK("gem");
     return MDS_OK;
 }
@@ -451,7 +467,7 @@ static int launch_linear(const float* feat, const float* w, const float* bias, f
                          cudaStream_t st) {
     if (b <= 0) return MDS_OK;
     ProfScope ps(MDS_KIND_HEAD, st);
-    linear_head_kernel<<<b, 256, 0, st>>>(feat, w, bias, out, F, k, sig);
+    launch_pdl(linear_head_kernel, dim3(b), dim3(256), 0, st, feat, w, bias, out, F, k, sig);
     LAUNCH_CHECK("linear_head");
     return MDS_OK;
 }

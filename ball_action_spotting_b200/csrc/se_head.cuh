@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
     float* s_mean = s_se;            // [C]
     float* s_hid = s_se + p.C;       // [rd]
     float* s_gate = s_hid + ((p.rd + 3) & ~3);   // [slice width]
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* part = p.partials + (size_t)n * p.nparts * p.C;
     for (int c = tid; c < p.C; c += kSeThreads) {      // fixed summation order; 4 loads in flight per step
@@ -140,6 +142,8 @@ struct GemParams {
 
 __global__ void __launch_bounds__(256) gem_kernel(GemParams g) {
     __shared__ float s_part[8][260];
+    pdl_trigger();
+    pdl_wait();
     const int t = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x;
     const int C8 = g.C >> 3;                 // threads along channels (8 ch each)
@@ -177,6 +181,8 @@ __global__ void __launch_bounds__(256) gem_kernel(GemParams g) {
 __global__ void __launch_bounds__(256) linear_head_kernel(const float* feat, const float* w, const float* bias, float* out,
                                                           int F, int num_classes, int apply_sigmoid) {
     __shared__ float s_red[8];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = 0; k < num_classes; ++k) {
         float acc = 0.f;

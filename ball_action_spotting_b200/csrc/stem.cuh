@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
     __shared__ __align__(16) __half s_in[kParts][3 * kStemPlane + 8];
     __shared__ __align__(16) __half s_stg[8][16 * kStemStgPitch];
 
+    pdl_trigger();
+    pdl_wait();       // the output buffer may still be read by the previous forward's last kernels
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int Ho = p.H >> 1, Wo = p.W >> 1;

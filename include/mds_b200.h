@@ -198,6 +198,10 @@ size_t mds_post_processing_workspace_bytes(int n_frames, int num_classes);
 int mds_post_processing(const float* raw, int n_frames, int num_classes, const double* weights_host, int radius, float height,
                         int distance, int* out_index, float* out_conf, int* out_count, void* ws, size_t ws_bytes, void* stream);
 
+/* Programmatic dependent launch of the forward chain (default on): each kernel's launch latency, CTA scheduling and
+ * constant set-up overlap the previous kernel's tail.  0 restores plain stream serialization (A/B measurements). */
+int mds_set_pdl(int enabled);
+
 /* number of kernels launched by this library in the calling thread since the last reset (bench "gpu_launches") */
 long long mds_launch_count(int reset);
 
