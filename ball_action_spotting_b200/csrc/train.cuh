@@ -103,6 +103,8 @@ __device__ __forceinline__ void ew_reduce_store(const EwParams& p, const EwCtx& 
 // BatchNorm batch statistics: partial sums of (y - ref) and (y - ref)^2, ref = p.mean = the layer's running mean (a
 // data-independent guess of the batch mean: the shift keeps the one-pass variance well conditioned).
 __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(EwParams p) {
+    pdl_trigger();
+    pdl_wait();
     const EwCtx c = ew_ctx(p);
     float acc[2][8] = {};
     if (c.active) {
@@ -138,6 +140,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(EwParams p) {
 // squeeze, multidim_stacker.py:86); 2: out = silu(z) * gate[sample] (:90); 3: out = z * mask[sample] + residual (:133).
 template <int MODE>
 __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(EwParams p) {
+    pdl_trigger();
+    pdl_wait();
     const EwCtx c = ew_ctx(p);
     float acc[1][8] = {};
     if (c.active) {
@@ -214,6 +218,8 @@ __device__ __forceinline__ void bwd_row(const BwdConst& k, const uint4& ry, cons
 // BatchNorm backward, pass 1: partial sums of dz and dz * yhat (d beta, d gamma)
 template <bool ACT>
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(EwParams p) {
+    pdl_trigger();
+    pdl_wait();
     const EwCtx c = ew_ctx(p);
     float acc[2][8] = {};
     if (c.active) {
@@ -248,6 +254,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(EwParams p) {
 // BatchNorm backward, pass 2: dy = gamma * rstd * (dz - mean(dz) - yhat * mean(dz * yhat))
 template <bool ACT>
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(EwParams p) {
+    pdl_trigger();
+    pdl_wait();
     const EwCtx c = ew_ctx(p);
     if (!c.active) return;
     BwdConst k;
@@ -278,6 +286,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(EwParams p) {
 
 // d gate[sample][c] = sum over the sample's rows of g * silu(bn(y))   (backward of x * gate, multidim_stacker.py:90)
 __global__ void __launch_bounds__(kEwThreads) dgate_kernel(EwParams p) {
+    pdl_trigger();
+    pdl_wait();
     const EwCtx c = ew_ctx(p);
     float acc[1][8] = {};
     if (c.active) {
@@ -331,6 +341,8 @@ struct BnFwdFin {
     int C; float count, eps, momentum;
 };
 __global__ void __launch_bounds__(kFinThreads) bn_fwd_finalize_kernel(BnFwdFin f) {
+    pdl_trigger();
+    pdl_wait();
     double tot[2];
     if (!fin_reduce<2>(f.partials, f.nparts, f.C, tot)) return;
     const int ch = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1));
@@ -360,11 +372,15 @@ struct BnBwdFin {
 };
 // per-sample column sums: out[b][c] = scale * sum_q partials[b][q][c]   (SE squeeze, d gate); grid (C / kFinCh, b)
 __global__ void __launch_bounds__(kFinThreads) colsum_finalize_kernel(const float* partials, int nparts, int C, float scale, float* out) {
+    pdl_trigger();
+    pdl_wait();
     double tot[1];
     if (!fin_reduce<1>(partials + (size_t)blockIdx.y * nparts * C, nparts, C, tot)) return;
     out[(size_t)blockIdx.y * C + blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1))] = (float)tot[0] * scale;
 }
 __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(BnBwdFin f) {
+    pdl_trigger();
+    pdl_wait();
     double tot[2];
     if (!fin_reduce<2>(f.partials, f.nparts, f.C, tot)) return;
     const int ch = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1));
@@ -382,6 +398,8 @@ __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(BnBwdFin f
 // ------------------------------------------------------------------------------------------------------------
 // fp32 master weight [C][27] -> tap-major [27][C] and its mirror (tap 26 - k)
 __global__ void __launch_bounds__(256) dw3_weights_kernel(const float* src, float* w27, float* w27_flip, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * 256 + threadIdx.x;      // i = k * C + c
     if (i >= 27 * C) return;
     const int k = i / C, c = i - k * C;
@@ -415,6 +433,8 @@ struct Dw3WgCfg {
 };
 
 __global__ void __launch_bounds__(256) dw3_wgrad_kernel(Dw3WgParams p) {
+    pdl_trigger();
+    pdl_wait();
     using Cfg = Dw3WgCfg;
     extern __shared__ __align__(16) unsigned char dwg_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -537,6 +557,8 @@ __global__ void __launch_bounds__(256) dw3_wgrad_kernel(Dw3WgParams p) {
 }
 // grad[c][tap] = sum over partials of partials[q][tap][c]
 __global__ void __launch_bounds__(256) dw3_wgrad_reduce_kernel(const float* partials, int nparts, int C, float* grad) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * 256 + threadIdx.x;      // i = tap * C + c
     if (i >= 27 * C) return;
     float s = 0.f;
@@ -560,6 +582,8 @@ struct WgradParams {
 constexpr int kWgBM = 32, kWgPitch = 72, kWgStages = 3;
 
 __global__ void __launch_bounds__(128) wgrad_gemm_kernel(WgradParams p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) __half s_a[kWgStages][kWgBM * kWgPitch];
     __shared__ __align__(16) __half s_b[kWgStages][kWgBM * kWgPitch];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -642,6 +666,8 @@ __global__ void __launch_bounds__(128) wgrad_gemm_kernel(WgradParams p) {
         }
 }
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* partials, int nparts, size_t count, float* out) {
+    pdl_trigger();
+    pdl_wait();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= count) return;
     float s = 0.f;
@@ -661,6 +687,8 @@ struct SeTrainParams {
 };
 // grid b, 256 threads, dynamic smem (2 * C + 2 * rd) floats
 __global__ void __launch_bounds__(256) se_train_fwd_kernel(SeTrainParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float s_se[];
     float* s_s = s_se;
     float* s_h = s_se + p.C;
@@ -686,6 +714,8 @@ __global__ void __launch_bounds__(256) se_train_fwd_kernel(SeTrainParams p) {
 }
 // grid b: d gate -> d(pre-sigmoid), d(pre-SiLU hidden), d squeeze / row count
 __global__ void __launch_bounds__(256) se_train_bwd_kernel(SeTrainParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float s_se[];
     float* s_dg = s_se;             // [C] d gpre
     float* s_dh = s_se + p.C;       // [rd] d hpre
@@ -721,6 +751,8 @@ struct SeGradParams {
     int b, C, rd;
 };
 __global__ void __launch_bounds__(256) se_train_wgrad_kernel(SeGradParams p) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * 256 + threadIdx.x;
     const int nW = p.C * p.rd;
     if (i < nW) {
@@ -761,6 +793,8 @@ struct GemTrainParams {
 };
 // grid (T, b, kGemChunks)
 __global__ void __launch_bounds__(256) gem_train_fwd_kernel(GemTrainParams g) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_part[2][8][260];
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int C8 = g.C >> 3, lanes_p = min(256 / C8, 8);
@@ -814,6 +848,8 @@ struct HeadTrainParams {
 // grid (ceil(F / 256), b), thread = one pooled feature: finish GeM (pooled, mlog, feat) and reduce this CTA's share of
 // the sample's logits into logit_partials[b][gridDim.x][K]
 __global__ void __launch_bounds__(256) head_logits_kernel(HeadTrainParams h) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_red[8];
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = blockIdx.x * 256 + tid;
@@ -848,6 +884,8 @@ __global__ void __launch_bounds__(256) head_logits_kernel(HeadTrainParams h) {
 // grid ceil(F / 256), thread = one pooled feature: focal loss gradient (recomputed per CTA from the b * K logits),
 // d classifier, d feat -> GeM backward coefficients, partial d p.  dynamic smem: 2 * b * K floats
 __global__ void __launch_bounds__(256) head_grad_kernel(HeadTrainParams h) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float s_dl[];          // [b][K] d loss / d logit (scaled), then [b][K] logits
     __shared__ float s_red[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -922,6 +960,8 @@ __global__ void __launch_bounds__(256) head_grad_kernel(HeadTrainParams h) {
     }
 }
 __global__ void head_dp_reduce_kernel(const float* partials, int n, float* out) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float a = 0.f;
     for (int i = 0; i < n; ++i) a += partials[i];
@@ -934,6 +974,8 @@ struct GemBwdParams {
     int T, P, C; float eps;
 };
 __global__ void __launch_bounds__(256) gem_bwd_kernel(GemBwdParams g) {
+    pdl_trigger();
+    pdl_wait();
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int C8 = g.C >> 3, lanes_p = 256 / C8;
     const int cg = tid % C8, pl = tid / C8;
@@ -958,6 +1000,8 @@ __global__ void __launch_bounds__(256) gem_bwd_kernel(GemBwdParams g) {
 // scaler[0] = loss scale, [1] = growth tracker, [2] = found_inf of this step, [3] = optimizer steps performed
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) grad_check_kernel(const float* grad, size_t count, float* scaler) {
+    pdl_trigger();
+    pdl_wait();
     bool bad = false;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (size_t)gridDim.x * 256)
         bad |= !isfinite(grad[i]);
@@ -965,6 +1009,8 @@ __global__ void __launch_bounds__(256) grad_check_kernel(const float* grad, size
 }
 __global__ void __launch_bounds__(256) sgd_nesterov_kernel(float* param, const float* grad, float* mom, size_t count,
                                                            const float* scaler, float lr, float momentum, int nesterov) {
+    pdl_trigger();
+    pdl_wait();
     if (scaler[2] != 0.0f) return;                        // GradScaler.step skips the update on inf / nan
     const float inv = 1.0f / scaler[0];
     const bool first = scaler[3] == 0.0f;                 // momentum buffer starts as a copy of the first gradient
@@ -977,6 +1023,8 @@ __global__ void __launch_bounds__(256) sgd_nesterov_kernel(float* param, const f
     }
 }
 __global__ void scaler_update_kernel(float* scaler, float growth, float backoff, float interval, int dynamic) {
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (scaler[2] != 0.0f) {
         if (dynamic) { scaler[0] *= backoff; scaler[1] = 0.0f; }
@@ -993,6 +1041,8 @@ __global__ void scaler_update_kernel(float* scaler, float growth, float backoff,
 // blockIdx.z selects the weight from a device table so that one launch refreshes all of them
 struct CastJob { const float* src; __half* dst; __half* dst_t; int R, Cc; };
 __global__ void __launch_bounds__(256) cast_transpose_kernel(const CastJob* jobs) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float tile[32][33];
     const CastJob j = jobs[blockIdx.z];
     const float* src = j.src; __half* dst = j.dst; __half* dst_t = j.dst_t;
@@ -1018,6 +1068,8 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const CastJob* jobs
 
 // counter-based Bernoulli masks (DropPath / Dropout) when the caller does not supply them: splitmix64 of (seed, index)
 __global__ void __launch_bounds__(256) bernoulli_mask_kernel(float* out, size_t count, float keep, unsigned long long seed) {
+    pdl_trigger();
+    pdl_wait();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= count) return;
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);

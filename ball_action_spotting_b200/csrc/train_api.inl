@@ -250,10 +250,10 @@ extern "C" int mds_train_scaler_state(MdsTrainer* t, float* host4) {
 
 static int train_derive(MdsTrainer* t, cudaStream_t st) {
     ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
-    cast_transpose_kernel<<<dim3(t->cast_gx, t->cast_gy, t->n_cast), 256, 0, st>>>(t->cast_jobs);
+    launch_pdl(cast_transpose_kernel, dim3(t->cast_gx, t->cast_gy, t->n_cast), dim3(256), 0, st, t->cast_jobs);
     LAUNCH_CHECK("cast_transpose");
     for (auto& b : t->blocks) {
-        dw3_weights_kernel<<<(27 * t->mid() + 255) / 256, 256, 0, st>>>(t->P + b.dw, b.dw27, b.dw27f, t->mid());
+        launch_pdl(dw3_weights_kernel, dim3((27 * t->mid() + 255) / 256), dim3(256), 0, st, t->P + b.dw, b.dw27, b.dw27f, t->mid());
         LAUNCH_CHECK("dw3_weights");
     }
     return MDS_OK;
@@ -311,7 +311,7 @@ static int train_bn_finalize(MdsTrainer* t, const TrainBn& bn, const float* part
     f.running_mean = t->S + bn.rm; f.running_var = t->S + bn.rv;
     f.scale = bn.scale(); f.shift = bn.shift(); f.mean = bn.mean(); f.rstd = bn.rstd();
     f.C = bn.C; f.count = (float)count; f.eps = 1e-5f; f.momentum = 0.1f;
-    bn_fwd_finalize_kernel<<<(bn.C + kFinCh - 1) / kFinCh, kFinThreads, 0, st>>>(f);
+    launch_pdl(bn_fwd_finalize_kernel, dim3((bn.C + kFinCh - 1) / kFinCh), dim3(kFinThreads), 0, st, f);
     LAUNCH_CHECK("bn_fwd_finalize");
     return MDS_OK;
 }
@@ -321,7 +321,7 @@ static int train_bn_stats(MdsTrainer* t, const TrainBn& bn, const __half* y, int
         ProfScope ps(MDS_KIND_TRAIN_BN, st);
         EwParams p = ew_base(y, bn.C, rows_per_sample, b);
         p.partials = partials; p.mean = t->S + bn.rm;
-        bn_stats_kernel<<<ew_grid(rows_per_sample, b), kEwThreads, 0, st>>>(p);
+        launch_pdl(bn_stats_kernel, ew_grid(rows_per_sample, b), dim3(kEwThreads), 0, st, p);
         LAUNCH_CHECK("bn_stats");
     }
     return train_bn_finalize(t, bn, partials, train_chunks(rows_per_sample, b) * b, (double)b * rows_per_sample, t->S + bn.rm, st);
@@ -333,7 +333,7 @@ static int train_bn_fwd(const TrainBn& bn, const __half* y, const __half* res, _
     ProfScope ps(MDS_KIND_TRAIN_BN, st);
     EwParams p = ew_base(y, bn.C, rows_per_sample, b);
     p.g = res; p.out = out; p.partials = partials; p.scale = bn.scale(); p.shift = bn.shift(); p.smul = smul; p.bmul = bmul;
-    bn_fwd_kernel<MODE><<<ew_grid(rows_per_sample, b), kEwThreads, 0, st>>>(p);
+    launch_pdl(bn_fwd_kernel<MODE>, ew_grid(rows_per_sample, b), dim3(kEwThreads), 0, st, p);
     LAUNCH_CHECK("bn_fwd");
     return MDS_OK;
 }
@@ -346,17 +346,17 @@ static int train_bn_bwd(MdsTrainer* t, const TrainBn& bn, bool act, const __half
     p.g = g; p.out = dy; p.partials = partials; p.scale = bn.scale(); p.shift = bn.shift(); p.mean = bn.mean(); p.rstd = bn.rstd();
     p.smul = smul; p.sadd = sadd; p.bmul = bmul; p.c1 = bn.c1(); p.c2 = bn.c2(); p.gr = bn.gr();
     const dim3 grid = ew_grid(rows_per_sample, b);
-    if (act) bn_bwd_reduce_kernel<true><<<grid, kEwThreads, 0, st>>>(p);
-    else bn_bwd_reduce_kernel<false><<<grid, kEwThreads, 0, st>>>(p);
+    if (act) launch_pdl(bn_bwd_reduce_kernel<true>, dim3(grid), dim3(kEwThreads), 0, st, p);
+    else launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(kEwThreads), 0, st, p);
     LAUNCH_CHECK("bn_bwd_reduce");
     BnBwdFin f;
     f.partials = partials; f.nparts = grid.x * b; f.gamma = t->P + bn.gamma; f.rstd = bn.rstd();
     f.dgamma = t->G + bn.gamma; f.dbeta = t->G + bn.beta; f.c1 = bn.c1(); f.c2 = bn.c2(); f.gr = bn.gr();
     f.C = bn.C; f.count = (float)((double)b * rows_per_sample);
-    bn_bwd_finalize_kernel<<<(bn.C + kFinCh - 1) / kFinCh, kFinThreads, 0, st>>>(f);
+    launch_pdl(bn_bwd_finalize_kernel, dim3((bn.C + kFinCh - 1) / kFinCh), dim3(kFinThreads), 0, st, f);
     LAUNCH_CHECK("bn_bwd_finalize");
-    if (act) bn_bwd_apply_kernel<true><<<grid, kEwThreads, 0, st>>>(p);
-    else bn_bwd_apply_kernel<false><<<grid, kEwThreads, 0, st>>>(p);
+    if (act) launch_pdl(bn_bwd_apply_kernel<true>, dim3(grid), dim3(kEwThreads), 0, st, p);
+    else launch_pdl(bn_bwd_apply_kernel<false>, dim3(grid), dim3(kEwThreads), 0, st, p);
     LAUNCH_CHECK("bn_bwd_apply");
     return MDS_OK;
 }
@@ -381,10 +381,10 @@ static int train_wgrad(const __half* dY, const __half* X, long long M, int N, in
     p.dY = dY; p.X = X; p.partials = partials; p.M = M; p.N = N; p.K = K;
     int splits = 1;
     wgrad_partial_floats(M, N, K, &splits, &p.rows_per_split);
-    wgrad_gemm_kernel<<<dim3(K / 64, N / 64, splits), 128, 0, st>>>(p);
+    launch_pdl(wgrad_gemm_kernel, dim3(K / 64, N / 64, splits), dim3(128), 0, st, p);
     LAUNCH_CHECK("wgrad_gemm");
     const size_t count = (size_t)N * K;
-    sum_partials_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(partials, splits, count, grad);
+    launch_pdl(sum_partials_kernel, dim3((unsigned)((count + 255) / 256)), dim3(256), 0, st, partials, splits, count, grad);
     LAUNCH_CHECK("sum_partials");
     return MDS_OK;
 }
@@ -420,7 +420,7 @@ static int train_dw3_conv(const __half* in, __half* out, const float* w27, const
         attr_set = true;
     }
     ProfScope ps(MDS_KIND_TRAIN_DW, st);
-    kern<<<dim3(p.xtiles * p.slabs, p.chunks * T, b), 256, Cfg::SMEM, st>>>(p);
+    launch_pdl(kern, dim3(p.xtiles * p.slabs, p.chunks * T, b), dim3(256), Cfg::SMEM, st, p);
     LAUNCH_CHECK("dwconv_lin");
     return MDS_OK;
 }
@@ -449,9 +449,9 @@ static int train_dw3_wgrad(const __half* in, const __half* dy, float* partials, 
         attr_set = true;
     }
     ProfScope ps(MDS_KIND_TRAIN_DW, st);
-    dw3_wgrad_kernel<<<dim3(p.xtiles * ((C + kDwCS - 1) / kDwCS), p.chunks * T, b), 256, Dw3WgCfg::SMEM, st>>>(p);
+    launch_pdl(dw3_wgrad_kernel, dim3(p.xtiles * ((C + kDwCS - 1) / kDwCS), p.chunks * T, b), dim3(256), Dw3WgCfg::SMEM, st, p);
     LAUNCH_CHECK("dw3_wgrad");
-    dw3_wgrad_reduce_kernel<<<(27 * C + 255) / 256, 256, 0, st>>>(partials, nparts, C, grad);
+    launch_pdl(dw3_wgrad_reduce_kernel, dim3((27 * C + 255) / 256), dim3(256), 0, st, partials, nparts, C, grad);
     LAUNCH_CHECK("dw3_wgrad_reduce");
     return MDS_OK;
 }
@@ -521,6 +521,8 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
     if (a->b <= 0 || a->b > 65535 || a->fh <= 0 || a->fw <= 0) return fail(MDS_ERR_INVALID, "train_step: bad batch / feature-map size");
     if ((long long)a->b * t->cfg.num_classes > 1024) return fail(MDS_ERR_INVALID, "train_step: b * num_classes must be <= 1024");
     DeviceGuard dg(t->cfg.device);
+    // measured: programmatic dependent launch slows this chain down (3.83 vs 3.66 ms per step), so it runs plainly serialized
+    struct PdlOff { bool prev; PdlOff() : prev(g_pdl) { g_pdl = false; } ~PdlOff() { g_pdl = prev; } } pdl_off;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int b = a->b, T = t->T(), P = a->fh * a->fw, rows = T * P;
     const int c3 = t->cfg.num_3d_features, mid = t->mid(), rd = t->rd(), pj = t->cfg.num_3d_stack_proj, nb = (int)t->blocks.size();
@@ -537,12 +539,12 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
     const float* dp_mask = a->dp_masks;
     const float* do_mask = a->dropout_mask;
     if (!dp_mask && t->cfg.drop_path_rate > 0.f && nb > 0) {
-        bernoulli_mask_kernel<<<(nb * b + 255) / 256, 256, 0, st>>>(w.dp_mask, (size_t)nb * b, 1.0f - t->cfg.drop_path_rate, a->seed * 2 + 1);
+        launch_pdl(bernoulli_mask_kernel, dim3((nb * b + 255) / 256), dim3(256), 0, st, w.dp_mask, (size_t)nb * b, 1.0f - t->cfg.drop_path_rate, a->seed * 2 + 1);
         LAUNCH_CHECK("bernoulli_mask");
         dp_mask = w.dp_mask;
     }
     if (!do_mask && t->cfg.drop_rate > 0.f) {
-        bernoulli_mask_kernel<<<(unsigned)(((size_t)b * F + 255) / 256), 256, 0, st>>>(w.do_mask, (size_t)b * F, 1.0f - t->cfg.drop_rate, a->seed * 2 + 2);
+        launch_pdl(bernoulli_mask_kernel, dim3((unsigned)(((size_t)b * F + 255) / 256)), dim3(256), 0, st, w.do_mask, (size_t)b * F, 1.0f - t->cfg.drop_rate, a->seed * 2 + 2);
         LAUNCH_CHECK("bernoulli_mask");
         do_mask = w.do_mask;
     }
@@ -567,14 +569,14 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
         TRY(train_bn_fwd<1>(B.bn2, w.y2[i], nullptr, nullptr, w.partials, nullptr, nullptr, b, rows, st));   // SE squeeze sums
         {
             ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
-            colsum_finalize_kernel<<<dim3((mid + kFinCh - 1) / kFinCh, b), kFinThreads, 0, st>>>(w.partials, train_chunks(rows, b), mid, inv_rows, se_s);
+            launch_pdl(colsum_finalize_kernel, dim3((mid + kFinCh - 1) / kFinCh, b), dim3(kFinThreads), 0, st, w.partials, train_chunks(rows, b), mid, inv_rows, se_s);
             LAUNCH_CHECK("colsum_finalize");
             SeTrainParams sp;
             memset(&sp, 0, sizeof(sp));
             sp.sums = se_s;
             sp.w1 = t->P + B.se_w1; sp.b1 = t->P + B.se_b1; sp.w2 = t->P + B.se_w2; sp.b2 = t->P + B.se_b2;
             sp.hpre = se_h; sp.gate = se_g; sp.C = mid; sp.rd = rd; sp.inv_count = inv_rows;
-            se_train_fwd_kernel<<<b, 256, se_smem, st>>>(sp);
+            launch_pdl(se_train_fwd_kernel, dim3(b), dim3(256), se_smem, st, sp);
             LAUNCH_CHECK("se_train_fwd");
         }
         TRY(train_bn_fwd<2>(B.bn2, w.y2[i], nullptr, w.a2g[i], nullptr, se_g, nullptr, b, rows, st));
@@ -591,7 +593,7 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
         ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
         GemTrainParams gp;
         gp.x = w.ap; gp.p = t->P + t->gem_p; gp.partials = w.gem_part; gp.T = T; gp.P = P; gp.C = pj; gp.eps = 1e-6f;
-        gem_train_fwd_kernel<<<dim3(T, b, kGemChunks), 256, 0, st>>>(gp);
+        launch_pdl(gem_train_fwd_kernel, dim3(T, b, kGemChunks), dim3(256), 0, st, gp);
         LAUNCH_CHECK("gem_train_fwd");
         HeadTrainParams hp;
         hp.gem_partials = w.gem_part; hp.feat = w.feat; hp.pooled = w.pooled; hp.mlog = w.mlog; hp.dmask = do_mask;
@@ -603,16 +605,16 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
         hp.b = b; hp.F = F; hp.K = K; hp.P = P; hp.C = pj; hp.alpha = t->cfg.focal_alpha; hp.gamma = t->cfg.focal_gamma;
         const int hblocks = (F + 255) / 256;
         hp.logit_partials = w.logit_part;
-        head_logits_kernel<<<dim3(hblocks, b), 256, 0, st>>>(hp);
+        launch_pdl(head_logits_kernel, dim3(hblocks, b), dim3(256), 0, st, hp);
         LAUNCH_CHECK("head_logits");
-        head_grad_kernel<<<hblocks, 256, (size_t)2 * b * K * sizeof(float), st>>>(hp);
+        launch_pdl(head_grad_kernel, dim3(hblocks), dim3(256), (size_t)2 * b * K * sizeof(float), st, hp);
         LAUNCH_CHECK("head_grad");
-        head_dp_reduce_kernel<<<1, 32, 0, st>>>(w.dp_part, hblocks, t->G + t->gem_p);
+        launch_pdl(head_dp_reduce_kernel, dim3(1), dim3(32), 0, st, w.dp_part, hblocks, t->G + t->gem_p);
         LAUNCH_CHECK("head_dp_reduce");
         // ============================================= backward =============================================
         GemBwdParams gb;
         gb.x = w.ap; gb.coef = w.coef; gb.p = t->P + t->gem_p; gb.dx = w.dP; gb.T = T; gb.P = P; gb.C = pj; gb.eps = 1e-6f;
-        gem_bwd_kernel<<<dim3(T, b, kGemChunks), 256, 0, st>>>(gb);
+        launch_pdl(gem_bwd_kernel, dim3(T, b, kGemChunks), dim3(256), 0, st, gb);
         LAUNCH_CHECK("gem_bwd");
     }
     g_prof_tag = 450;
@@ -633,12 +635,12 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
             ProfScope ps(MDS_KIND_TRAIN_BN, st);
             EwParams p = ew_base(w.y2[i], mid, rows, b);
             p.g = w.DM1; p.partials = w.partials; p.scale = B.bn2.scale(); p.shift = B.bn2.shift();
-            dgate_kernel<<<ew_grid(rows, b), kEwThreads, 0, st>>>(p);
+            launch_pdl(dgate_kernel, ew_grid(rows, b), dim3(kEwThreads), 0, st, p);
             LAUNCH_CHECK("dgate");
         }
         {
             ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
-            colsum_finalize_kernel<<<dim3((mid + kFinCh - 1) / kFinCh, b), kFinThreads, 0, st>>>(w.partials, train_chunks(rows, b), mid, 1.0f, w.se_sum);
+            launch_pdl(colsum_finalize_kernel, dim3((mid + kFinCh - 1) / kFinCh, b), dim3(kFinThreads), 0, st, w.partials, train_chunks(rows, b), mid, 1.0f, w.se_sum);
             LAUNCH_CHECK("colsum_finalize");
             SeTrainParams sp;
             memset(&sp, 0, sizeof(sp));
@@ -646,13 +648,13 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
             sp.w1 = t->P + B.se_w1; sp.b1 = t->P + B.se_b1; sp.w2 = t->P + B.se_w2; sp.b2 = t->P + B.se_b2;
             sp.hpre = se_h; sp.gate = se_g; sp.dgpre = w.se_dg; sp.dhpre = w.se_dh; sp.sadd = w.se_sadd;
             sp.C = mid; sp.rd = rd; sp.inv_count = inv_rows;
-            se_train_bwd_kernel<<<b, 256, se_smem, st>>>(sp);
+            launch_pdl(se_train_bwd_kernel, dim3(b), dim3(256), se_smem, st, sp);
             LAUNCH_CHECK("se_train_bwd");
             SeGradParams sg;
             sg.s = se_s; sg.hpre = se_h; sg.dgpre = w.se_dg; sg.dhpre = w.se_dh;
             sg.dw1 = t->G + B.se_w1; sg.db1 = t->G + B.se_b1; sg.dw2 = t->G + B.se_w2; sg.db2 = t->G + B.se_b2;
             sg.b = b; sg.C = mid; sg.rd = rd;
-            se_train_wgrad_kernel<<<(mid * rd + 255) / 256, 256, 0, st>>>(sg);
+            launch_pdl(se_train_wgrad_kernel, dim3((mid * rd + 255) / 256), dim3(256), 0, st, sg);
             LAUNCH_CHECK("se_train_wgrad");
         }
         TRY(train_bn_bwd(t, B.bn2, true, w.y2[i], w.DM1, w.DM2, se_g, w.se_sadd, nullptr, b, rows, w.partials, st));   // -> d y2
@@ -673,11 +675,11 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
         {
             ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
             const int blocks = (int)((t->n_params + 255) / 256) < 4 * num_sms() ? (int)((t->n_params + 255) / 256) : 4 * num_sms();
-            grad_check_kernel<<<blocks, 256, 0, st>>>(t->G, t->n_params, t->scaler);
+            launch_pdl(grad_check_kernel, dim3(blocks), dim3(256), 0, st, t->G, t->n_params, t->scaler);
             LAUNCH_CHECK("grad_check");
-            sgd_nesterov_kernel<<<blocks, 256, 0, st>>>(t->P, t->G, t->Mom, t->n_params, t->scaler, a->lr, t->cfg.momentum, t->cfg.nesterov);
+            launch_pdl(sgd_nesterov_kernel, dim3(blocks), dim3(256), 0, st, t->P, t->G, t->Mom, t->n_params, t->scaler, a->lr, t->cfg.momentum, t->cfg.nesterov);
             LAUNCH_CHECK("sgd_nesterov");
-            scaler_update_kernel<<<1, 32, 0, st>>>(t->scaler, 2.0f, 0.5f, 2000.0f, t->cfg.amp);
+            launch_pdl(scaler_update_kernel, dim3(1), dim3(32), 0, st, t->scaler, 2.0f, 0.5f, 2000.0f, t->cfg.amp);
             LAUNCH_CHECK("scaler_update");
         }
         TRY(train_derive(t, st));
