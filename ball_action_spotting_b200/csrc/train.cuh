@@ -40,8 +40,8 @@ struct EwParams {
     const float* smul;      // [samples][C] or nullptr (SE gate)
     const float* sadd;      // [samples][C] or nullptr (SE squeeze gradient, already divided by the row count)
     const float* bmul;      // [samples]    or nullptr (DropPath mask)
-    const float* c1;        // [C] sum(dz) / M
-    const float* c2;        // [C] sum(dz * yhat) / M
+    const float* c1;        // [C] A   (backward pass 2: dy = gr * dz + A * y + B)
+    const float* c2;        // [C] B
     const float* gr;        // [C] gamma * rstd
     int C, rows_per_sample, rows_per_chunk;
 };
@@ -182,17 +182,19 @@ __global__ void __launch_bounds__(kEwThreads) bn_fwd_kernel(EwParams p) {
     if (MODE == 1) ew_reduce_store<1>(p, c, acc);
 }
 
-// incoming gradient of the BatchNorm(+SiLU) output for one row: da = g * smul + sadd, times the DropPath mask
+// incoming gradient of the BatchNorm(+SiLU) output for one row: da = g * smul + sadd, times the DropPath mask.
+// The per-channel constants live in registers, so the kernels keep as few of them as the algebra allows:
+//   pass 1 accumulates sum(dz) and sum(dz * (y - mean))            -> needs scale, shift (for z) and mean
+//   pass 2 writes dy = gr * dz + A * y + B, with A = -rstd * gr * c2 and B = -gr * c1 - mean * A folded by the finalize
+//   kernel (gr = gamma * rstd, c1 = sum(dz) / M, c2 = sum(dz * yhat) / M)   -> needs scale, shift, gr, A, B
 struct BwdConst {
-    float sc[8], sh[8], mu[8], rs[8], sm[8], sa[8];
+    float sc[8], sh[8], sm[8], sa[8];
     float bm;
     bool has_s;
 };
 __device__ __forceinline__ void bwd_load_const(const EwParams& p, const EwCtx& c, BwdConst& k) {
     load8(p.scale, c.cg, k.sc);
     load8(p.shift, c.cg, k.sh);
-    load8(p.mean, c.cg, k.mu);
-    load8(p.rstd, c.cg, k.rs);
     k.has_s = p.smul != nullptr;
     if (k.has_s) {
         load8(p.smul + (size_t)c.smp * p.C, c.cg, k.sm);
@@ -201,8 +203,8 @@ __device__ __forceinline__ void bwd_load_const(const EwParams& p, const EwCtx& c
     k.bm = p.bmul ? __ldg(p.bmul + c.smp) : 1.0f;
 }
 template <bool ACT>
-__device__ __forceinline__ void bwd_row(const BwdConst& k, const uint4& ry, const uint4& rg, float (&dz)[8], float (&yh)[8]) {
-    float v[8], g[8];
+__device__ __forceinline__ void bwd_row(const BwdConst& k, const uint4& ry, const uint4& rg, float (&dz)[8], float (&v)[8]) {
+    float g[8];
     half8_to_float(ry, v);
     half8_to_float(rg, g);
 #pragma unroll
@@ -210,12 +212,12 @@ __device__ __forceinline__ void bwd_row(const BwdConst& k, const uint4& ry, cons
         float da = g[i];
         if (k.has_s) da = fmaf(da, k.sm[i], k.sa[i]);
         da *= k.bm;
-        yh[i] = (v[i] - k.mu[i]) * k.rs[i];
         dz[i] = ACT ? da * dsilu_f(fmaf(v[i], k.sc[i], k.sh[i])) : da;
     }
 }
+constexpr int kBwdRows = 4;      // rows (pairs of 16-byte loads) in flight per thread
 
-// BatchNorm backward, pass 1: partial sums of dz and dz * yhat (d beta, d gamma)
+// BatchNorm backward, pass 1: partial sums of dz and dz * (y - mean)   (d beta, d gamma / rstd)
 template <bool ACT>
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(EwParams p) {
     pdl_trigger();
@@ -225,25 +227,24 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(EwParams p) {
     if (c.active) {
         BwdConst k;
         bwd_load_const(p, c, k);
-        const uint4 zero = make_uint4(0, 0, 0, 0);
-        for (int r = c.r0 + c.rl; r < c.r1; r += 2 * c.RL) {
-            const bool two = r + c.RL < c.r1;
-            const uint4 ya = ldg_row(p.y, c.base + r, p.C, c.cg), ga = ldg_row(p.g, c.base + r, p.C, c.cg);
-            const uint4 yb = two ? ldg_row(p.y, c.base + r + c.RL, p.C, c.cg) : zero;
-            const uint4 gb = two ? ldg_row(p.g, c.base + r + c.RL, p.C, c.cg) : zero;
-            float dz[8], yh[8];
-            bwd_row<ACT>(k, ya, ga, dz, yh);
+        float mu[8];
+        load8(p.mean, c.cg, mu);
+        for (int r = c.r0 + c.rl; r < c.r1; r += kBwdRows * c.RL) {
+            uint4 ry[kBwdRows], rg[kBwdRows];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                acc[0][i] += dz[i];
-                acc[1][i] = fmaf(dz[i], yh[i], acc[1][i]);
+            for (int u = 0; u < kBwdRows; ++u) {
+                const int rr = r + u * c.RL;
+                if (rr < c.r1) { ry[u] = ldg_row(p.y, c.base + rr, p.C, c.cg); rg[u] = ldg_row(p.g, c.base + rr, p.C, c.cg); }
             }
-            if (two) {
-                bwd_row<ACT>(k, yb, gb, dz, yh);
+#pragma unroll
+            for (int u = 0; u < kBwdRows; ++u) {
+                if (r + u * c.RL >= c.r1) break;
+                float dz[8], v[8];
+                bwd_row<ACT>(k, ry[u], rg[u], dz, v);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     acc[0][i] += dz[i];
-                    acc[1][i] = fmaf(dz[i], yh[i], acc[1][i]);
+                    acc[1][i] = fmaf(dz[i], v[i] - mu[i], acc[1][i]);
                 }
             }
         }
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(EwParams p) {
     ew_reduce_store<2>(p, c, acc);
 }
 
-// BatchNorm backward, pass 2: dy = gamma * rstd * (dz - mean(dz) - yhat * mean(dz * yhat))
+// BatchNorm backward, pass 2: dy = gamma * rstd * (dz - mean(dz) - yhat * mean(dz * yhat)) = gr * dz + A * y + B
 template <bool ACT>
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(EwParams p) {
     pdl_trigger();
@@ -260,26 +261,26 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(EwParams p) {
     if (!c.active) return;
     BwdConst k;
     bwd_load_const(p, c, k);
-    float c1[8], c2[8], gr[8];
-    load8(p.c1, c.cg, c1);
-    load8(p.c2, c.cg, c2);
+    float ca[8], cb[8], gr[8];
+    load8(p.c1, c.cg, ca);       // A (see bn_bwd_finalize_kernel)
+    load8(p.c2, c.cg, cb);       // B
     load8(p.gr, c.cg, gr);
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int r = c.r0 + c.rl; r < c.r1; r += 2 * c.RL) {
-        const bool two = r + c.RL < c.r1;
-        const uint4 ya = ldg_row(p.y, c.base + r, p.C, c.cg), ga = ldg_row(p.g, c.base + r, p.C, c.cg);
-        const uint4 yb = two ? ldg_row(p.y, c.base + r + c.RL, p.C, c.cg) : zero;
-        const uint4 gb = two ? ldg_row(p.g, c.base + r + c.RL, p.C, c.cg) : zero;
-        float dz[8], yh[8], o[8];
-        bwd_row<ACT>(k, ya, ga, dz, yh);
+    for (int r = c.r0 + c.rl; r < c.r1; r += kBwdRows * c.RL) {
+        uint4 ry[kBwdRows], rg[kBwdRows];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = gr[i] * (dz[i] - c1[i] - yh[i] * c2[i]);
-        store_row8(p.out, c.base + r, p.C, c.cg, o);
-        if (two) {
-            bwd_row<ACT>(k, yb, gb, dz, yh);
+        for (int u = 0; u < kBwdRows; ++u) {
+            const int rr = r + u * c.RL;
+            if (rr < c.r1) { ry[u] = ldg_row(p.y, c.base + rr, p.C, c.cg); rg[u] = ldg_row(p.g, c.base + rr, p.C, c.cg); }
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = gr[i] * (dz[i] - c1[i] - yh[i] * c2[i]);
-            store_row8(p.out, c.base + r + c.RL, p.C, c.cg, o);
+        for (int u = 0; u < kBwdRows; ++u) {
+            const int rr = r + u * c.RL;
+            if (rr >= c.r1) break;
+            float dz[8], v[8], o[8];
+            bwd_row<ACT>(k, ry[u], rg[u], dz, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaf(gr[i], dz[i], fmaf(ca[i], v[i], cb[i]));
+            store_row8(p.out, c.base + rr, p.C, c.cg, o);
         }
     }
 }
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kFinThreads) bn_fwd_finalize_kernel(BnFwdFin f
 
 struct BnBwdFin {
     const float* partials; int nparts;
-    const float *gamma, *rstd;
+    const float *gamma, *rstd, *mean;
     float *dgamma, *dbeta;        // gradient slices (still multiplied by the loss scale)
     float *c1, *c2, *gr;
     int C; float count;
@@ -384,11 +385,15 @@ __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(BnBwdFin f
     double tot[2];
     if (!fin_reduce<2>(f.partials, f.nparts, f.C, tot)) return;
     const int ch = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1));
+    const double rstd = (double)f.rstd[ch], gr = (double)f.gamma[ch] * rstd;
+    const double dgamma = tot[1] * rstd;                    // pass 1 accumulated dz * (y - mean)
     f.dbeta[ch] = (float)tot[0];
-    f.dgamma[ch] = (float)tot[1];
-    f.c1[ch] = (float)(tot[0] / (double)f.count);
-    f.c2[ch] = (float)(tot[1] / (double)f.count);
-    f.gr[ch] = f.gamma[ch] * f.rstd[ch];
+    f.dgamma[ch] = (float)dgamma;
+    const double c1 = tot[0] / (double)f.count, c2 = dgamma / (double)f.count;
+    const double A = -rstd * gr * c2;
+    f.c1[ch] = (float)A;                                    // dy = gr * dz + A * y + B
+    f.c2[ch] = (float)(-gr * c1 - (double)f.mean[ch] * A);
+    f.gr[ch] = (float)gr;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -350,7 +350,7 @@ static int train_bn_bwd(MdsTrainer* t, const TrainBn& bn, bool act, const __half
     else launch_pdl(bn_bwd_reduce_kernel<false>, dim3(grid), dim3(kEwThreads), 0, st, p);
     LAUNCH_CHECK("bn_bwd_reduce");
     BnBwdFin f;
-    f.partials = partials; f.nparts = grid.x * b; f.gamma = t->P + bn.gamma; f.rstd = bn.rstd();
+    f.partials = partials; f.nparts = grid.x * b; f.gamma = t->P + bn.gamma; f.rstd = bn.rstd(); f.mean = bn.mean();
     f.dgamma = t->G + bn.gamma; f.dbeta = t->G + bn.beta; f.c1 = bn.c1(); f.c2 = bn.c2(); f.gr = bn.gr();
     f.C = bn.C; f.count = (float)((double)b * rows_per_sample);
     launch_pdl(bn_bwd_finalize_kernel, dim3((bn.C + kFinCh - 1) / kFinCh), dim3(kFinThreads), 0, st, f);
@@ -363,7 +363,7 @@ static int train_bn_bwd(MdsTrainer* t, const TrainBn& bn, bool act, const __half
 
 static size_t wgrad_partial_floats(long long M, int N, int K, int* splits_out, int* rows_out) {
     const int tiles = (N / 64) * (K / 64);
-    int want = (2 * num_sms() + tiles - 1) / tiles;
+    int want = (4 * num_sms() + tiles - 1) / tiles;       // ~4 CTAs of 128 threads per SM hide the smem / L2 latency
     if (want < 1) want = 1;
     long long rows = (M + want - 1) / want;
     rows = (rows + 31) / 32 * 32;
