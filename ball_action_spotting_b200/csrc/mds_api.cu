@@ -452,14 +452,19 @@ static int launch_se(const float* partials, int nparts, const float* w1, const f
     return MDS_OK;
 }
 
-static int launch_gem(const __half* x, float* feat, int b, int T, int P, int C, float pw, float eps, cudaStream_t st) {
+static size_t gem_part_floats(int b, int T, int C) { return (size_t)b * T * kGemSplit * C; }
+static int launch_gem(const __half* x, float* feat, float* part, int b, int T, int P, int C, float pw, float eps, cudaStream_t st) {
     if (C % 8 || C > 256 || C < 32) return fail(MDS_ERR_INVALID, "gem: C must be a multiple of 8 in [32, 256]");
     if (b <= 0) return MDS_OK;
+    if (b > 65535) return fail(MDS_ERR_INVALID, "gem: b too large");
     GemParams g;
-    g.x = x; g.feat = feat; g.T = T; g.P = P; g.C = C; g.p = pw; g.eps = eps;
+    g.x = x; g.part = part; g.feat = feat; g.T = T; g.P = P; g.C = C; g.p = pw; g.eps = eps;
     ProfScope ps(MDS_KIND_HEAD, st);
-    launch_pdl(gem_kernel, dim3(T, b), dim3(256), 0, st, g);
+    launch_pdl(gem_kernel, dim3(T, b, kGemSplit), dim3(256), 0, st, g);
     LAUNCH_CHECK("gem");
+    const int total = b * T * C;
+    launch_pdl(gem_finish_kernel, dim3((total + 255) / 256), dim3(256), 0, st, g, total);
+    LAUNCH_CHECK("gem_finish");
     return MDS_OK;
 }
 
@@ -717,7 +722,9 @@ static size_t ws3d_bytes(const MdsHandle* h, int b, int P) {
            al256((size_t)b * kDwMaxParts * h->mid3d() * 4) + al256((size_t)b * h->mid3d() * 2) +
            al256((size_t)b * h->cfg.num_3d_features * h->mid3d() * 2);
 }
-static size_t wshead_bytes(const MdsHandle* h, int b) { return al256((size_t)b * h->cfg.num_3d_stack_proj * h->T() * 4); }
+static size_t wshead_bytes(const MdsHandle* h, int b) {
+    return al256((size_t)b * h->cfg.num_3d_stack_proj * h->T() * 4) + al256(gem_part_floats(b, h->T(), h->cfg.num_3d_stack_proj) * 4);
+}
 
 extern "C" size_t mds_workspace_bytes(const MdsHandle* h, int H, int W, int n_images, int n_stacks) {
     if (!h) return 0;
@@ -836,9 +843,10 @@ static int forward_head_impl(MdsHandle* h, const __half* x, int b, int P, float*
     if (b <= 0) return MDS_OK;
     const int T = h->T(), pj = h->cfg.num_3d_stack_proj;
     float* feat = ar.take<float>((size_t)b * T * pj);
+    float* part = ar.take<float>(gem_part_floats(b, T, pj));
     if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_head: workspace too small");
     g_prof_tag = 200;
-    TRY(launch_gem(x, feat, b, T, P, pj, h->gem_p, 1e-6f, st));
+    TRY(launch_gem(x, feat, part, b, T, P, pj, h->gem_p, 1e-6f, st));
     TRY(launch_linear(feat, h->cls_w, h->cls_b, logits, b, T * pj, h->cfg.num_classes, sig, st));
     return MDS_OK;
 }
@@ -977,7 +985,14 @@ extern "C" int mds_k_gemm_gated(const void* A, const void* wg, const void* bias_
                                  reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int mds_k_gem(const void* x, float* feat, int b, int T, int P, int C, float p, float eps, void* stream) {
-    return launch_gem(reinterpret_cast<const __half*>(x), feat, b, T, P, C, p, eps, reinterpret_cast<cudaStream_t>(stream));
+    // per-kernel entry point (tests): the slice sums need scratch, allocated here stream-ordered
+    float* part = nullptr;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (b <= 0) return MDS_OK;
+    CUDA_TRY(cudaMallocAsync(&part, gem_part_floats(b, T, C) * sizeof(float), st));
+    const int rc = launch_gem(reinterpret_cast<const __half*>(x), feat, part, b, T, P, C, p, eps, st);
+    CUDA_TRY(cudaFreeAsync(part, st));
+    return rc;
 }
 extern "C" int mds_k_linear(const float* feat, const float* w, const float* bias, float* out, int b, int F, int num_classes,
                             int apply_sigmoid, void* stream) {

@@ -133,8 +133,12 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
 }
 
 // GeM (multidim_stacker.py:42-45) over the P = h*w positions of x[b][t][P][C]: feat[b][t*C + c].
+// Two launches: partial sums of clamp(x, eps)^p over kGemSplit slices of the positions (grid (T, b, kGemSplit): enough
+// CTAs to hide the latency at small batches), then the fixed-order sum, mean and ^(1/p).
+constexpr int kGemSplit = 8;
 struct GemParams {
     const __half* x;   // [b][T][P][C]
+    float* part;       // [b][T][kGemSplit][C]
     float* feat;       // [b][T*C]
     int T, P, C;
     float p, eps;
@@ -150,10 +154,12 @@ __global__ void __launch_bounds__(256) gem_kernel(GemParams g) {
     const int lanes_p = min(256 / C8, 8);    // position lanes (s_part holds 8)
     const int cg = tid % C8, pl = tid / C8;
     const bool cube = (g.p == 3.0f);
+    const int per = (g.P + kGemSplit - 1) / kGemSplit;
+    const int p0 = blockIdx.z * per, p1 = min(g.P, p0 + per);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const __half* base = g.x + (((size_t)b * g.T + t) * g.P) * g.C + cg * 8;
     if (pl < lanes_p) {
-        for (int pos = pl; pos < g.P; pos += lanes_p) {
+        for (int pos = p0 + pl; pos < p1; pos += lanes_p) {
             float v[8];
             half8_to_float(ldg16(base + (size_t)pos * g.C), v);
 #pragma unroll
@@ -162,9 +168,6 @@ __global__ void __launch_bounds__(256) gem_kernel(GemParams g) {
                 acc[i] += cube ? x * x * x : powf(x, g.p);
             }
         }
-    }
-    // reduce over position lanes through smem (C <= 256, lanes_p <= 8)
-    if (pl < lanes_p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) s_part[pl][cg * 8 + i] = acc[i];
     }
@@ -172,9 +175,21 @@ __global__ void __launch_bounds__(256) gem_kernel(GemParams g) {
     if (tid < g.C) {
         float s = 0.f;
         for (int l = 0; l < lanes_p; ++l) s += s_part[l][tid];
-        float m = s / (float)g.P;
-        g.feat[(size_t)b * g.T * g.C + (size_t)t * g.C + tid] = cube ? cbrtf(m) : powf(m, 1.0f / g.p);
+        g.part[(((size_t)b * g.T + t) * kGemSplit + blockIdx.z) * g.C + tid] = s;
     }
+}
+// grid ceil(b * T * C / 256): feat = (sum of the slices / P)^(1/p)
+__global__ void __launch_bounds__(256) gem_finish_kernel(GemParams g, int total) {
+    pdl_trigger();
+    pdl_wait();
+    const int i = blockIdx.x * 256 + threadIdx.x;         // i = (b * T + t) * C + c
+    if (i >= total) return;
+    const int bt = i / g.C, c = i - bt * g.C;
+    float s = 0.f;
+#pragma unroll
+    for (int z = 0; z < kGemSplit; ++z) s += g.part[((size_t)bt * kGemSplit + z) * g.C + c];
+    const float m = s / (float)g.P;
+    g.feat[i] = (g.p == 3.0f) ? cbrtf(m) : powf(m, 1.0f / g.p);
 }
 
 // logits[b][k] = feat[b] . W[k] + bias[k]  (nn.Linear, multidim_stacker.py:236); optional sigmoid (argus_models.py:26)
