@@ -56,9 +56,53 @@ def load_model(model_path, device: str = "cuda:0") -> LoadedModel:
     return LoadedModel(params, module, dev)
 
 
+class _FrameGraphs:
+    """CUDA graphs of the two fixed-shape pieces of one ``predict`` call: (1) encoder of the newest 3-frame triple,
+    (2) 3D blocks + head over the window of cached features.  One call launches ~90 kernels of a few microseconds each and
+    is bound by the host (0.97 ms of launch + Python work per frame vs 1.09 ms total), so the launch sequence is recorded
+    once and replayed; inputs and outputs live at fixed addresses."""
+
+    def __init__(self, predictor: "MultiDimStackerPredictor", h: int, w: int):
+        dev = predictor.device
+        eng = predictor.model.nn_module.engine(dev)
+        W, H = predictor.image_size
+        n_tta = 2 if predictor.tta else 1
+        T = predictor.frame_stack_size // predictor.model_stack_size
+        self.frames = torch.zeros((predictor.model_stack_size, h, w), dtype=torch.uint8, device=dev)
+        self.stack = torch.zeros((n_tta, T, H // 32, W // 32, 192), dtype=torch.float16, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up outside capture: workspaces, kernel attributes
+            for _ in range(2):
+                predictor._encode(eng, self.frames)
+                predictor._head(eng, self.stack)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.g2d = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g2d):
+            self.feat = predictor._encode(eng, self.frames)              # (n_tta, fh, fw, 192) fp16
+        self.g3d = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g3d):
+            self.pred = predictor._head(eng, self.stack)                 # (num_classes,) float32
+        self._ws = eng._ws          # the recorded launches point into this workspace: keep it alive if the engine grows a new one
+
+    def encode(self, frames) -> torch.Tensor:
+        for i, f in enumerate(frames):
+            self.frames[i].copy_(f)
+        self.g2d.replay()
+        return self.feat.clone()
+
+    def head(self, feats) -> torch.Tensor:
+        for j, f in enumerate(feats):
+            self.stack[:, j].copy_(f)
+        self.g3d.replay()
+        return self.pred.clone()
+
+
 class MultiDimStackerPredictor:
-    def __init__(self, model_path: Path, device: str = "cuda:0", tta: bool = False):
+    def __init__(self, model_path: Path, device: str = "cuda:0", tta: bool = False, cuda_graph: bool = True):
         self.model = load_model(model_path, device=device)
+        self.cuda_graph = cuda_graph
+        self._graphs: Optional[_FrameGraphs] = None
         self.model.eval()
         self.device = self.model.device
         self.tta = tta
@@ -86,16 +130,23 @@ class MultiDimStackerPredictor:
         for stack_indexes in [s for s in self._stack_indexes2features if any(i < minimum_index for i in s)]:
             del self._stack_indexes2features[stack_indexes]
 
-    def _features_2d(self, stack_indexes) -> torch.Tensor:
-        eng = self.model.nn_module.engine(self.device)
-        frames = torch.stack([self._frame_index2frame[i] for i in stack_indexes], dim=0)   # (3, h, W) uint8
+    def _encode(self, eng, frames: torch.Tensor) -> torch.Tensor:
+        """frames (3, h, W) uint8 -> cached features (n_tta, fh, fw, 192) fp16 (predictors.py:60-66; the TTA flip is the
+        stem kernel reading mirrored columns, :63)."""
         h, w = frames.shape[-2:]
         W, H = self.image_size
         outs = []
         for flip in ((False, True) if self.tta else (False,)):
             desc = eng.frames_desc(frames, H, W, 3 * h * w, h * w, hflip=flip)
             outs.append(eng.forward_2d(desc, 1))                           # (1, fh, fw, 192) fp16
-        return torch.cat(outs, dim=0)                                      # (B_tta, fh, fw, 192)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def _head(self, eng, feats: torch.Tensor) -> torch.Tensor:
+        """feats (n_tta, T, fh, fw, 192) -> probabilities (num_classes,) (predictors.py:69-72)."""
+        prediction = eng.forward_head(eng.forward_3d(feats), sigmoid=True)  # prediction_transform fused
+        if prediction.shape[0] == 2:                                       # TTA: mean of the two branches (:72)
+            return eng.axpby_(prediction[0], prediction[1], 0.5, 0.5)
+        return prediction[0]
 
     @torch.no_grad()
     def predict(self, frame: torch.Tensor, index: int):
@@ -107,17 +158,17 @@ class MultiDimStackerPredictor:
         predict_indexes = self.indexes_generator.make_stack_indexes(predict_index)
         self._clear_old(predict_indexes[0])
         if set(predict_indexes) <= set(self._frame_index2frame.keys()):
+            eng = self.model.nn_module.engine(self.device)
+            if self.cuda_graph and (self._graphs is None or self._graphs.frames.shape[-2:] != frame.shape[-2:]):
+                self._graphs = _FrameGraphs(self, frame.shape[-2], frame.shape[-1])
             stacks_indexes = list(batched(predict_indexes, self.model_stack_size))
             for stack_indexes in stacks_indexes:
                 if stack_indexes not in self._stack_indexes2features:
-                    self._stack_indexes2features[stack_indexes] = self._features_2d(stack_indexes)
-            feats = torch.stack([self._stack_indexes2features[s] for s in stacks_indexes], dim=1)  # (B, T, fh, fw, 192)
-            eng = self.model.nn_module.engine(self.device)
-            x = eng.forward_3d(feats.contiguous())
-            prediction = eng.forward_head(x, sigmoid=True)                 # prediction_transform fused
-            if prediction.shape[0] == 2:                                   # TTA: mean of the two branches (predictors.py:72)
-                prediction = eng.axpby_(prediction[0], prediction[1], 0.5, 0.5)
-            else:
-                prediction = prediction[0]
-            return prediction, predict_index
+                    triple = [self._frame_index2frame[i] for i in stack_indexes]
+                    self._stack_indexes2features[stack_indexes] = (
+                        self._graphs.encode(triple) if self.cuda_graph else self._encode(eng, torch.stack(triple, dim=0)))
+            cached = [self._stack_indexes2features[s] for s in stacks_indexes]     # T x (n_tta, fh, fw, 192)
+            if self.cuda_graph:
+                return self._graphs.head(cached), predict_index
+            return self._head(eng, torch.stack(cached, dim=1).contiguous()), predict_index
         return None, predict_index

@@ -252,3 +252,33 @@ def test_batched_sweep_equals_streaming_predictor(tmp_path, oracle_sd, tta):
     assert (batch[0] - ref).abs().max().item() <= tol_for(96, 160)
     with pytest.raises(RuntimeError, match="need frames"):
         sweep.predict_range(frames, 0, 10, 12)
+
+
+@pytest.mark.parametrize("tta", [False, True])
+def test_streaming_predictor_cuda_graph_equals_eager(tmp_path, oracle_sd, tta):
+    """predict() replays two CUDA graphs (encoder of the new triple; 3D blocks + head); the recorded launches are the
+    same kernels as the eager path, so the probabilities are bit-identical, also after reset_buffers()."""
+    from ball_action_spotting_b200 import MultiDimStackerPredictor
+    params = {"nn_module": ("multidim_stacker", dict(model_name="tf_efficientnetv2_b0.in1k", num_classes=2, num_frames=15,
+                                                     stack_size=3, index_2d_features=4, pretrained=False, num_3d_blocks=4,
+                                                     num_3d_features=192, expansion_3d_ratio=3, se_reduce_3d_ratio=24,
+                                                     num_3d_stack_proj=256, drop_rate=0.2, drop_path_rate=0.2, act_layer="silu")),
+              "frames_processor": ("pad_normalize", {"size": (320, 192), "pad_mode": "constant", "fill_value": 0}),
+              "frame_stack_size": 15, "frame_stack_step": 2}
+    path = tmp_path / "model.pth"
+    torch.save({"model_name": "BallActionModel", "params": params, "nn_state_dict": oracle_sd}, path)
+    graphed = MultiDimStackerPredictor(path, device=DEV, tta=tta)
+    eager = MultiDimStackerPredictor(path, device=DEV, tta=tta, cuda_graph=False)
+    frames = torch.randint(0, 256, (40, 180, 320), dtype=torch.uint8, generator=torch.Generator().manual_seed(4)).to(DEV)
+    for rnd in range(2):
+        n = 0
+        for i in range(40):
+            a, ia = graphed.predict(frames[i], i)
+            b, ib = eager.predict(frames[i], i)
+            assert ia == ib and (a is None) == (b is None)
+            if a is not None:
+                n += 1
+                assert torch.equal(a, b), (rnd, i, a.tolist(), b.tolist())
+        assert n == 40 - 28
+        graphed.reset_buffers()
+        eager.reset_buffers()
