@@ -33,6 +33,11 @@ def test_forward_backward_matches_oracle(cfg, b, hw):
     _check(TP.compare(cfg, b, hw))
 
 
+def test_wide_feature_map_uses_column_tiles_and_row_chunks():
+    """43 columns -> two 40-column tiles in the depthwise kernels; 13 rows -> several row chunks in the weight gradient."""
+    _check(TP.compare(O.ModelConfig(num_frames=9), 2, (13, 43)))
+
+
 def test_forward_backward_without_drops():
     _check(TP.compare(O.ModelConfig(num_frames=9), 3, (5, 7), drop=False))
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn gpurun_out/*.ncu-rep + launches csv into committed text summaries under profiles/.
-    python tools/ncu_summarize.py r01 gpurun_out/prof_*.ncu-rep [--launches gpurun_out/launches_b4.csv]"""
+    python tools/ncu_summarize.py r01 gpurun_out/prof_*.ncu-rep [--launches gpurun_out/launches_b4.csv] [--workload TEXT]"""
 import csv
 import subprocess
 import sys
@@ -31,10 +31,14 @@ def main():
         i = args.index("--launches")
         launches = args[i + 1]
         args = args[:i] + args[i + 2:]
+    workload = "tools/ncu_target.py 16 (FULL forward, 16 stacks = 80 images)"
+    if "--workload" in args:
+        i = args.index("--workload")
+        workload = args[i + 1]
+        args = args[:i] + args[i + 2:]
     out_dir = ROOT / "profiles"
     out_dir.mkdir(exist_ok=True)
-    lines = [f"# ncu --set full --clock-control none, one launch per kernel (round {tag}); workload: tools/ncu_target.py 16 "
-             "(FULL forward, 16 stacks = 80 images)", ""]
+    lines = [f"# ncu --set full --clock-control none, one launch per kernel (round {tag}); workload: {workload}", ""]
     for rep in args:
         hdr, units, vals = raw(rep)
         name = vals[hdr.index("Kernel Name")]
