@@ -69,6 +69,7 @@ SIGNATURES = {
     "mds_train_set": (_i, [_vp, C.c_char_p, _vp, C.c_longlong]),
     "mds_train_get": (_i, [_vp, C.c_char_p, _i, _vp, C.c_longlong]),
     "mds_train_commit": (_i, [_vp, _vp]),
+    "mds_train_ema_update": (_i, [_vp, C.c_double, _vp]),
     "mds_train_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "mds_train_step": (_i, [_vp, C.POINTER(MdsTrainStepArgs), _vp, _sz, _vp]),
     "mds_train_scaler_state": (_i, [_vp, _vp]),

@@ -1042,6 +1042,14 @@ __global__ void scaler_update_kernel(float* scaler, float growth, float backoff,
     }
     scaler[2] = 0.0f;
 }
+// ModelEma.update (src/ema.py:49-57): ema = decay * ema + (1 - decay) * value, in the reference's float32 arithmetic
+// (two rounded products, one rounded sum -- no fused multiply-add, so the result is bit-identical to torch)
+__global__ void __launch_bounds__(256) ema_update_kernel(float* ema, const float* cur, size_t count, float decay, float one_minus) {
+    pdl_trigger();
+    pdl_wait();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (size_t)gridDim.x * 256)
+        ema[i] = __fadd_rn(__fmul_rn(decay, ema[i]), __fmul_rn(one_minus, cur[i]));
+}
 // fp32 master weight [R][Cc] -> fp16 copy and fp16 transposed copy [Cc][R] (operands of the forward / dgrad GEMMs);
 // blockIdx.z selects the weight from a device table so that one launch refreshes all of them
 struct CastJob { const float* src; __half* dst; __half* dst_t; int R, Cc; };

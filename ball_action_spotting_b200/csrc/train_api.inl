@@ -38,6 +38,7 @@ struct MdsTrainer {
     std::vector<TrainTensor> params, buffers;
     std::map<std::string, int> pindex, bindex;
     size_t n_params = 0, n_stats = 0;
+    float *Pema = nullptr, *Sema = nullptr;      // ModelEma copies of the parameters / BatchNorm statistics (src/ema.py)
     float *P = nullptr, *G = nullptr, *Mom = nullptr, *S = nullptr, *scaler = nullptr, *bn_scratch = nullptr, *zeros = nullptr, *dw27 = nullptr;
     __half* w16 = nullptr;
     CastJob* cast_jobs = nullptr;   // device table of the fp16 operand refreshes (one launch)
@@ -132,6 +133,8 @@ extern "C" int mds_train_create(const MdsTrainConfig* cfg, MdsTrainer** out) {
     if (e == cudaSuccess) e = alloc((void**)&t->G, t->n_params * 4);
     if (e == cudaSuccess) e = alloc((void**)&t->Mom, t->n_params * 4);
     if (e == cudaSuccess) e = alloc((void**)&t->S, t->n_stats * 4);
+    if (e == cudaSuccess) e = alloc((void**)&t->Pema, t->n_params * 4);
+    if (e == cudaSuccess) e = alloc((void**)&t->Sema, t->n_stats * 4);
     if (e == cudaSuccess) e = alloc((void**)&t->scaler, 16);
     if (e == cudaSuccess) e = alloc((void**)&t->bn_scratch, bn_floats * 4);
     if (e == cudaSuccess) e = alloc((void**)&t->zeros, 1152 * 4);
@@ -180,7 +183,7 @@ extern "C" int mds_train_create(const MdsTrainConfig* cfg, MdsTrainer** out) {
 extern "C" int mds_train_destroy(MdsTrainer* t) {
     if (!t) return MDS_OK;
     DeviceGuard g(t->cfg.device);
-    cudaFree(t->P); cudaFree(t->G); cudaFree(t->Mom); cudaFree(t->S); cudaFree(t->scaler); cudaFree(t->bn_scratch);
+    cudaFree(t->P); cudaFree(t->G); cudaFree(t->Mom); cudaFree(t->S); cudaFree(t->Pema); cudaFree(t->Sema); cudaFree(t->scaler); cudaFree(t->bn_scratch);
     cudaFree(t->zeros); cudaFree(t->w16); cudaFree(t->dw27); cudaFree(t->zeros16); cudaFree(t->cast_jobs);
     delete t;
     return MDS_OK;
@@ -226,10 +229,11 @@ extern "C" int mds_train_get(MdsTrainer* t, const char* name, int what, float* h
     bool is_param; const TrainTensor* tt;
     TRY(train_find(t, name, numel, &is_param, &tt));
     if (!host) return fail(MDS_ERR_INVALID, "train_get: null data");
-    if (!is_param && what != 0) return fail(MDS_ERR_INVALID, "train_get: buffers have no gradient / momentum");
+    if (!is_param && what != 0 && what != 3) return fail(MDS_ERR_INVALID, "train_get: buffers have no gradient / momentum");
+    if (what < 0 || what > 3) return fail(MDS_ERR_INVALID, "train_get: what must be 0..3");
     DeviceGuard g(t->cfg.device);
     CUDA_TRY(cudaDeviceSynchronize());
-    const float* src = !is_param ? t->S : what == 0 ? t->P : what == 1 ? t->G : t->Mom;
+    const float* src = !is_param ? (what == 3 ? t->Sema : t->S) : what == 0 ? t->P : what == 1 ? t->G : what == 2 ? t->Mom : t->Pema;
     CUDA_TRY(cudaMemcpy(host, src + tt->off, (size_t)numel * 4, cudaMemcpyDeviceToHost));
     if (is_param && what == 1) {       // gradients are stored multiplied by the loss scale
         float sc[4];
@@ -262,8 +266,30 @@ static int train_derive(MdsTrainer* t, cudaStream_t st) {
 extern "C" int mds_train_commit(MdsTrainer* t, void* stream) {
     if (!t) return fail(MDS_ERR_INVALID, "null trainer");
     DeviceGuard g(t->cfg.device);
-    TRY(train_derive(t, reinterpret_cast<cudaStream_t>(stream)));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TRY(train_derive(t, st));
+    // ModelEma(model) deep-copies the model it is given (src/ema.py:38-41): the averages start from the committed values
+    CUDA_TRY(cudaMemcpyAsync(t->Pema, t->P, t->n_params * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(t->Sema, t->S, t->n_stats * 4, cudaMemcpyDeviceToDevice, st));
     t->committed = true;
+    return MDS_OK;
+}
+
+extern "C" int mds_train_ema_update(MdsTrainer* t, double decay, void* stream) {
+    if (!t) return fail(MDS_ERR_INVALID, "null trainer");
+    if (!t->committed) return fail(MDS_ERR_WEIGHTS, "train_ema_update: parameters not committed");
+    if (!(decay >= 0.0 && decay <= 1.0)) return fail(MDS_ERR_INVALID, "train_ema_update: decay must be in [0, 1]");
+    DeviceGuard g(t->cfg.device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // the reference evaluates `self.decay * e + (1. - self.decay) * m` with a Python (double) decay on float32 tensors:
+    // both scalars are rounded to float32 separately
+    const float decay32 = (float)decay, one_minus = (float)(1.0 - decay);
+    ProfScope ps(MDS_KIND_TRAIN_SMALL, st);
+    const int blocks = (int)((t->n_params + 255) / 256) < 4 * num_sms() ? (int)((t->n_params + 255) / 256) : 4 * num_sms();
+    ema_update_kernel<<<blocks, 256, 0, st>>>(t->Pema, t->P, t->n_params, decay32, one_minus);
+    LAUNCH_CHECK("ema_update");
+    ema_update_kernel<<<(unsigned)((t->n_stats + 255) / 256), 256, 0, st>>>(t->Sema, t->S, t->n_stats, decay32, one_minus);
+    LAUNCH_CHECK("ema_update");
     return MDS_OK;
 }
 

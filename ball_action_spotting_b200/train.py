@@ -33,7 +33,8 @@ class FrozenEncoderTrainer:
 
     def __init__(self, model: MultiDimStacker, lr: float, momentum: float = 0.9, nesterov: bool = True,
                  focal_alpha: float = 0.4, focal_gamma: float = 1.2, amp: bool = True,
-                 drop_rate: Optional[float] = None, drop_path_rate: float = 0.2, init_scale: float = 65536.0):
+                 drop_rate: Optional[float] = None, drop_path_rate: float = 0.2, init_scale: float = 65536.0,
+                 ema_decay: Optional[float] = None):
         self.lib = _lib.load()
         self.model = model
         dev = model.classifier.weight.device
@@ -42,6 +43,8 @@ class FrozenEncoderTrainer:
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         cfg = model._cfg
         self.lr = float(lr)
+        self.ema_decay = ema_decay        # ModelEma decay (configs: ema_decay=0.999); None = no averaging
+        self._ema_tracked = None
         self.cfg = MdsTrainConfig(
             cfg.num_classes, cfg.num_frames, cfg.stack_size, cfg.num_3d_blocks, cfg.num_3d_features, cfg.num_3d_stack_proj,
             cfg.expansion_3d_ratio, cfg.se_reduce_3d_ratio, self.device.index, 1 if amp else 0, 1 if nesterov else 0,
@@ -54,6 +57,7 @@ class FrozenEncoderTrainer:
         self._step = 0
         self.param_names = self._names(0)
         self.buffer_names = self._names(1)
+        self._tracked_base = int(model.state_dict()[next(k for k in model.state_dict() if k.startswith('conv3d_projection') and k.endswith('num_batches_tracked'))])
         self.load_from_module()
 
     def _names(self, kind: int) -> Dict[str, int]:
@@ -86,12 +90,12 @@ class FrozenEncoderTrainer:
         check(self.lib.mds_train_commit(self._h, torch.cuda.current_stream(self.device).cuda_stream), "mds_train_commit")
 
     def get(self, name: str, what: str = "value") -> torch.Tensor:
-        """what: 'value' | 'grad' (of the last step, unscaled) | 'momentum'.  Flat float32 CPU tensor."""
+        """what: 'value' | 'grad' (of the last step, unscaled) | 'momentum' | 'ema'.  Flat float32 CPU tensor."""
         numel = self.param_names.get(name, self.buffer_names.get(name))
         if numel is None:
             raise KeyError(name)
         out = torch.empty(numel, dtype=torch.float32)
-        check(self.lib.mds_train_get(self._h, name.encode(), {"value": 0, "grad": 1, "momentum": 2}[what], out.data_ptr(), numel),
+        check(self.lib.mds_train_get(self._h, name.encode(), {"value": 0, "grad": 1, "momentum": 2, "ema": 3}[what], out.data_ptr(), numel),
               f"mds_train_get({name})")
         return out
 
@@ -108,6 +112,31 @@ class FrozenEncoderTrainer:
                     sd[k].add_(tracked - getattr(self, "_tracked_synced", 0))
         self._tracked_synced = tracked
         self.model.repack()
+
+    def ema_update(self) -> None:
+        """``self.model_ema.update(self.nn_module)`` (argus_models.py:68-69, src/ema.py:49-57)."""
+        if self.ema_decay is None:
+            raise RuntimeError("ema_update: the trainer was created without ema_decay")
+        check(self.lib.mds_train_ema_update(self._h, float(self.ema_decay), torch.cuda.current_stream(self.device).cuda_stream),
+              "mds_train_ema_update")
+        # num_batches_tracked is an integer buffer: ModelEma averages it in float and copy_ truncates (src/ema.py:47)
+        tracked = int(self.lib.mds_train_batches_tracked(self._h)) + self._tracked_base
+        if self._ema_tracked is None:
+            self._ema_tracked = self._tracked_base
+        self._ema_tracked = int((torch.tensor(float(self.ema_decay)) * self._ema_tracked + torch.tensor(1.0 - float(self.ema_decay)) * tracked).item())
+
+    def ema_state_dict(self) -> Dict[str, torch.Tensor]:
+        """state_dict of ``model_ema.ema`` (what EmaCheckpoint stores as ``nn_state_dict``, src/ema.py:61-76): averaged trainable
+        parameters and BatchNorm statistics; the frozen encoder is constant, so its entries equal the module's."""
+        sd = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        for name in list(self.param_names) + list(self.buffer_names):
+            sd[name] = self.get(name, "ema").view(sd[name].shape).to(sd[name].device)
+        if self._ema_tracked is not None:
+            for name in self.buffer_names:
+                if name.endswith("running_mean"):
+                    k = name[: -len("running_mean")] + "num_batches_tracked"
+                    sd[k] = torch.tensor(self._ema_tracked, dtype=torch.long, device=sd[k].device)
+        return sd
 
     def scaler_state(self) -> Tuple[float, float, float, float]:
         out = (C.c_float * 4)()
@@ -172,4 +201,6 @@ class FrozenEncoderTrainer:
         frames = frames.to(self.device, non_blocking=True)
         target = target.to(self.device, non_blocking=True)
         loss, logits = self.step_on_features(self.encoder_features(frames), target)
+        if self.ema_decay is not None:
+            self.ema_update()
         return {"prediction": torch.sigmoid(logits), "target": target, "loss": loss.item()}     # prediction_transform (:26,69)

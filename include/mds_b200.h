@@ -178,9 +178,12 @@ int mds_train_destroy(MdsTrainer* t);
 int mds_train_num_tensors(const MdsTrainer* t, int kind);
 int mds_train_tensor_info(const MdsTrainer* t, int kind, int i, const char** name, long long* numel);
 int mds_train_set(MdsTrainer* t, const char* name, const float* host, long long numel);
-/* what 0: value, 1: gradient of the last step (unscaled), 2: momentum buffer; synchronises the device */
+/* what 0: value, 1: gradient of the last step (unscaled), 2: momentum buffer, 3: ModelEma average; synchronises the device */
 int mds_train_get(MdsTrainer* t, const char* name, int what, float* host, long long numel);
-int mds_train_commit(MdsTrainer* t, void* stream);     /* after mds_train_set: derive the fp16 GEMM operands */
+int mds_train_commit(MdsTrainer* t, void* stream);     /* after mds_train_set: derive the fp16 GEMM operands, re-seed the EMA */
+/* ModelEma.update (src/ema.py:49-57; argus_models.py:68-69): ema = decay * ema + (1 - decay) * value for every trainable
+ * parameter and BatchNorm statistic, in the reference's float32 arithmetic. */
+int mds_train_ema_update(MdsTrainer* t, double decay, void* stream);
 size_t mds_train_workspace_bytes(const MdsTrainer* t, int b, int fh, int fw);
 int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* args, void* ws, size_t ws_bytes, void* stream);
 /* host4: loss scale, growth tracker, found_inf flag, optimizer steps performed; synchronises the device */

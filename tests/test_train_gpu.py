@@ -130,3 +130,30 @@ def test_internal_masks_and_train_step_api():
     f = tr.encoder_features(frames.to(DEV))
     assert f.shape == (2, 3, 3, 5, 192) and torch.isfinite(f.float()).all()
     tr.close()
+
+
+def test_model_ema_follows_the_reference_recursion():
+    """ModelEma.update (src/ema.py:49-57): ema = decay * ema + (1 - decay) * value in float32, seeded with the initial model;
+    bit-exact against the same recursion evaluated by torch on the parameter values read back after every step."""
+    cfg, b, hw, decay = O.ModelConfig(num_frames=9), 2, (4, 5), 0.9
+    sd = O.make_state_dict(cfg, seed=1234, calib_hw=(96, 160))
+    from ball_action_spotting_b200 import FrozenEncoderTrainer
+    net, tr0 = TP.build(cfg, sd)
+    tr0.close()
+    tr = FrozenEncoderTrainer(net, lr=0.05, ema_decay=decay)
+    names = ["conv3d_encoder.1.conv_pw.weight", "classifier.bias", "global_pool.p", "conv3d_encoder.0.bn2.bn3d.running_var"]
+    ema = {k: tr.get(k).clone() for k in names}
+    for k in names:
+        assert torch.equal(tr.get(k, "ema"), ema[k])              # seeded with a copy of the model
+    for step in range(3):
+        enc, targets = TO.make_case(cfg, b, hw, seed=300 + step)
+        tr.step_on_features(TP.to_nhwc16(enc, b, cfg.num_stacks), targets)
+        tr.ema_update()
+        for k in names:
+            ema[k] = decay * ema[k] + (1.0 - decay) * tr.get(k)
+            assert torch.equal(tr.get(k, "ema"), ema[k]), (step, k)
+    esd = tr.ema_state_dict()
+    assert set(esd) == set(net.state_dict())
+    assert torch.equal(esd["classifier.bias"].cpu(), ema["classifier.bias"])
+    assert int(esd["conv3d_encoder.0.bn1.bn3d.num_batches_tracked"]) == int(0.9 * int(0.9 * int(0.9 * 0 + 0.1 * 1) + 0.1 * 2) + 0.1 * 3)
+    tr.close()
