@@ -62,6 +62,32 @@ def cpu_forward_timer(steps: int, warmup: int):
     return times, cores
 
 
+def train_step_cpu_baseline(sd, frames: int, b: int, fhw, steps: int):
+    """cpu_baseline leg of tools/bench_train.py (BASELINE.json configs[4]): the training-step oracle (reference modules
+    restated, torch CPU fp32 autograd + SGD) on the box's host cores, same batch shape as the GPU step."""
+    import torch
+    from oracle import mds_oracle as O                  # baseline legs only
+    from oracle import mds_train_oracle as TO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.ModelConfig(num_frames=frames)
+    enc, tg = TO.make_case(cfg, b, tuple(fhw), seed=7)
+    dp, do = TO.make_masks(cfg, b, 0.2, 0.2, 11)
+    bufs, times = {}, []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        _, _, grads, stats = TO.loss_and_grads(sd, enc, tg, cfg, dp, do)
+        params = {k: sd[k] for k in grads}
+        TO.sgd_nesterov_step(params, grads, bufs, 1e-3)
+        sd.update(params)
+        sd.update(stats)
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return {"ms_per_step": ms, "frame_stacks_per_s": 1e3 * b / ms, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} timed + 1 warm-up 3D-only steps (fwd+bwd+SGD) of the same batch, torch CPU fp32 autograd"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:

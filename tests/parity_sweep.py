@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Distribution of the end-to-end logit error over N full-size stacks (GPU engine vs CPU fp32 oracle).
-    python tools/parity_sweep.py [N] [seed]"""
+    python tests/parity_sweep.py [N] [seed]
+Lives under tests/ because it uses the oracle as the checker."""
 import json
 import sys
 from pathlib import Path

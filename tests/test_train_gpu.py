@@ -10,7 +10,7 @@ import torch
 
 from oracle import mds_oracle as O
 from oracle import mds_train_oracle as TO
-from tools import train_parity as TP
+import train_parity as TP
 
 pytestmark = pytest.mark.gpu
 GRAD_TOL, LOSS_TOL, LOGIT_TOL, STAT_TOL = 2e-2, 2e-3, 5e-3, 2e-3

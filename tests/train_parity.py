@@ -1,7 +1,7 @@
 """Parity of the CUDA training step (mds_train_step) against the CPU fp32 oracle, tensor by tensor.
 
-Usage (GPU box): python tools/train_parity.py            # prints a table for a few shapes
-Imported by tests/test_train_gpu.py.  The oracle is the checker only.
+Usage (GPU box): python tests/train_parity.py            # prints a table for a few shapes
+Test helper (imported by tests/test_train_gpu.py); lives under tests/ because it uses the oracle as the checker.
 """
 from __future__ import annotations
 

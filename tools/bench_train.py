@@ -10,7 +10,7 @@ Reports, as one JSON object:
 * ``by_kind``: share of the step per kernel class from the library's CUDA-event hooks, with the achieved HBM GB/s of
   the BatchNorm column kernels and the TFLOP/s of the GEMMs (algorithmic bytes / flops stated in DESIGN.md §10);
 * ``cpu_baseline``: the oracle (reference modules restated, torch CPU fp32, all host threads) on the same step.
-The oracle is used only as the timed baseline.
+The timed CPU baseline is bench.py's `train_step_cpu_baseline` (oracle port).
 """
 from __future__ import annotations
 
@@ -121,27 +121,10 @@ def main():
            "scaler": tr.scaler_state()}
 
     if args.cpu_steps > 0:
-        from oracle import mds_oracle as O            # timed baseline only
-        from oracle import mds_train_oracle as TO
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        cfg = O.ModelConfig(num_frames=args.frames)
+        import bench                                   # the CPU-baseline leg (the only code that executes oracle/) lives in bench.py
         sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
-        enc, tg = TO.make_case(cfg, b, (fh, fw), seed=7)
-        dp, do = TO.make_masks(cfg, b, 0.2, 0.2, 11)
-        bufs, times = {}, []
-        for i in range(args.cpu_steps + 1):
-            t0 = time.perf_counter()
-            _, _, grads, stats = TO.loss_and_grads(sd, enc, tg, cfg, dp, do)
-            params = {k: sd[k] for k in grads}
-            TO.sgd_nesterov_step(params, grads, bufs, 1e-3)
-            sd.update(params); sd.update(stats)
-            if i > 0:
-                times.append(time.perf_counter() - t0)
-        cpu_ms = 1e3 * sum(times) / len(times)
-        out["cpu_baseline"] = {"ms_per_step": cpu_ms, "frame_stacks_per_s": 1e3 * b / cpu_ms, "cores": cores, "kind": "port",
-                               "sample": f"{len(times)} timed + 1 warm-up 3D-only steps (fwd+bwd+SGD) of the same batch, torch CPU fp32 autograd"}
-        out["speedup_step_3d_vs_cpu"] = cpu_ms / ms_3d
+        out["cpu_baseline"] = bench.train_step_cpu_baseline(sd, args.frames, b, (fh, fw), args.cpu_steps)
+        out["speedup_step_3d_vs_cpu"] = out["cpu_baseline"]["ms_per_step"] / ms_3d
     s = json.dumps(out, indent=1)
     print(s)
     if args.out:
