@@ -103,6 +103,19 @@ extern "C" int mds_profile_end(int* kinds, int* tags, float* ms, int capacity, i
     return MDS_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: set it once per (kernel, device)
+constexpr int kMaxDevices = 64;
+#define ENSURE_SMEM_ATTR(kern, bytes)                                                                           \
+    do {                                                                                                        \
+        static bool done_[kMaxDevices] = {};                                                                    \
+        int dev_ = 0;                                                                                           \
+        cudaGetDevice(&dev_);                                                                                   \
+        if (dev_ >= 0 && dev_ < kMaxDevices && !done_[dev_]) {                                                  \
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));    \
+            done_[dev_] = true;                                                                                 \
+        }                                                                                                       \
+    } while (0)
+
 // Launch with programmatic stream serialization (see pdl_trigger / pdl_wait in common.cuh)
 static bool g_pdl = !(getenv("MDS_PDL") && getenv("MDS_PDL")[0] == '0');     // MDS_PDL=0: plain stream serialization
 template <typename... KArgs, typename... Args>
@@ -168,11 +181,7 @@ template <int CIN, int CMID, int STRIDE, int CPROJ, bool RES, int MINB, int MT>
 static int launch_conv3_t(const Conv3Params& p, cudaStream_t st) {
     using Cfg = Conv3Cfg<CIN, CMID, STRIDE, CPROJ, RES>;
     auto kern = conv3x3_kernel<CIN, CMID, STRIDE, CPROJ, RES, MINB, MT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
     const int tiles = ((p.Wo + Cfg::TW - 1) / Cfg::TW) * ((p.Ho + Cfg::TH - 1) / Cfg::TH) * p.n;
     if (tiles <= 0) return MDS_OK;
     int grid = num_sms() * MINB;
@@ -206,11 +215,7 @@ static int launch_conv3_tc(const __half* in, __half* out, const __half* w1, cons
     const long long tiles = (long long)p.tiles_x * p.tiles_y * n;
     if (tiles <= 0) return MDS_OK;
     auto kern = conv3x3_tc_kernel<CIN, CMID, COUT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
     int grid = num_sms();
     if (tiles < grid) grid = (int)tiles;
     ProfScope ps(MDS_KIND_CONV3X3, st);
@@ -244,11 +249,7 @@ template <int BN, bool GATED>
 static int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm1x1_kernel<BN, GATED>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
     const int tiles_per_img = (p.rows_per_img + kGemmBM - 1) / kGemmBM;
     dim3 grid((p.N + BN - 1) / BN, tiles_per_img * p.n_img);
     if (grid.y > 65535) return fail(MDS_ERR_INVALID, "gemm1x1: too many M tiles (%u)", grid.y);
@@ -302,10 +303,14 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     p.stages = tc_stages(p.BN, p.streamed);
     const size_t smem = tc_smem_bytes(p.BN, p.streamed);
     if (smem > 227 * 1024) return fail(MDS_ERR_INVALID, "gemm_tc: BN=%d needs %zu bytes of shared memory", p.BN, smem);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    {   // the opt-in limit is a per-device attribute: track the largest value set on each device
+        static size_t smem_set[kMaxDevices] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < kMaxDevices && smem > smem_set[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[dev] = smem;
+        }
     }
     int grid = num_sms();
     if (p.m_tiles < grid) grid = p.m_tiles;
@@ -388,11 +393,7 @@ template <int KT, int STRIDE>
 static int launch_dw_t(const DwParams& p, dim3 grid, cudaStream_t st) {
     using Cfg = DwCfg<KT, STRIDE>;
     auto kern = dwconv_kernel<KT, STRIDE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
     ProfScope ps(KT == 1 ? MDS_KIND_DWCONV2D : MDS_KIND_DWCONV3D, st);
     launch_pdl(kern, grid, dim3(256), Cfg::SMEM, st, p);
     LAUNCH_CHECK("dwconv");

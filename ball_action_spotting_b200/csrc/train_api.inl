@@ -440,11 +440,7 @@ static int train_dw3_conv(const __half* in, __half* out, const float* w27, const
     if (nparts_total) *nparts_total = p.nparts * b;
     using Cfg = DwCfg<3, 1>;
     auto kern = dwconv_kernel<3, 1, true>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
     ProfScope ps(MDS_KIND_TRAIN_DW, st);
     launch_pdl(kern, dim3(p.xtiles * p.slabs, p.chunks * T, b), dim3(256), Cfg::SMEM, st, p);
     LAUNCH_CHECK("dwconv_lin");
@@ -469,11 +465,7 @@ static int train_dw3_wgrad(const __half* in, const __half* dy, float* partials, 
     p.in = in; p.dy = dy; p.partials = partials; p.n = b; p.T = T; p.H = H; p.W = W; p.C = C;
     p.xtiles = (W + kDwTWX - 1) / kDwTWX;
     const int nparts = dw3_wgrad_geometry(b, T, H, W, C, &p.chunks, &p.rows_per_chunk);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(dw3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Dw3WgCfg::SMEM));
-        attr_set = true;
-    }
+    ENSURE_SMEM_ATTR(dw3_wgrad_kernel, Dw3WgCfg::SMEM);
     ProfScope ps(MDS_KIND_TRAIN_DW, st);
     launch_pdl(dw3_wgrad_kernel, dim3(p.xtiles * ((C + kDwCS - 1) / kDwCS), p.chunks * T, b), dim3(256), Dw3WgCfg::SMEM, st, p);
     LAUNCH_CHECK("dw3_wgrad");

@@ -282,3 +282,21 @@ def test_streaming_predictor_cuda_graph_equals_eager(tmp_path, oracle_sd, tta):
         assert n == 40 - 28
         graphed.reset_buffers()
         eager.reset_buffers()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(oracle_sd):
+    """One process driving cuda:0 and cuda:1 (the reference's scripts pick the device by --gpu_id): the per-device kernel
+    attributes and handles are independent, and both devices produce the same bits."""
+    cfg = O.ModelConfig()
+    x = torch.randint(0, 256, (2, 15, 96, 160), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        from ball_action_spotting_b200 import MultiDimStacker
+        net = MultiDimStacker("tf_efficientnetv2_b0.in1k", cfg.num_classes, num_frames=cfg.num_frames, stack_size=3,
+                              num_3d_blocks=cfg.num_3d_blocks, expansion_3d_ratio=cfg.expansion_3d_ratio,
+                              se_reduce_3d_ratio=cfg.se_reduce_3d_ratio)
+        net.load_state_dict(oracle_sd)
+        net.to(dev).eval()
+        outs.append(net(x.to(dev)).cpu())
+    assert torch.equal(outs[0], outs[1])
