@@ -34,7 +34,7 @@ constexpr int kStemPlane = kStemIH * kStemIWP;                          // halve
 constexpr int kStemStgPitch = 40;                                       // halves per pixel in the output staging tile
 
 template <typename IN_T>
-__global__ void __launch_bounds__(256, 2) stem_kernel(StemParams p) {
+__global__ void __launch_bounds__(256, 3) stem_kernel(StemParams p) {   // 3 CTAs / SM: measured 7 % faster than 2 (106 -> 80 registers), 4 spills
     constexpr bool kFloat = sizeof(IN_T) == 4;
     constexpr int kParts = kFloat ? 2 : 1;                // float input is split into fp16 hi + lo
     __shared__ __align__(16) __half s_in[kParts][3 * kStemPlane + 8];
