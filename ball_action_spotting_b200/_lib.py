@@ -74,6 +74,7 @@ SIGNATURES = {
     "mds_train_step": (_i, [_vp, C.POINTER(MdsTrainStepArgs), _vp, _sz, _vp]),
     "mds_train_scaler_state": (_i, [_vp, _vp]),
     "mds_train_batches_tracked": (C.c_longlong, [_vp]),
+    "mds_focal_loss": (_i, [_vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "mds_post_processing_workspace_bytes": (_sz, [_i, _i]),
     "mds_post_processing": (_i, [_vp, _i, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mds_set_pdl": (_i, [_i]),

@@ -973,6 +973,26 @@ __global__ void head_dp_reduce_kernel(const float* partials, int n, float* out) 
     out[0] = a;
 }
 
+// sigmoid focal loss (src/losses.py:31-48, mean reduction) and the sigmoid probabilities of a small logit matrix: the
+// validation step (BallActionModel.val_step, src/argus_models.py:76-91).  One CTA; the sum runs in a fixed order.
+__global__ void __launch_bounds__(256) focal_loss_kernel(const float* logits, const float* targets, int n, float alpha, float gamma,
+                                                         float* loss, float* probs) {
+    pdl_trigger();
+    pdl_wait();
+    for (int o = threadIdx.x; o < n; o += 256) probs[o] = 1.0f / (1.0f + expf(-logits[o]));
+    if (threadIdx.x != 0) return;
+    float total = 0.f;
+    for (int o = 0; o < n; ++o) {
+        const float x = logits[o], t = targets[o];
+        const float pr = 1.0f / (1.0f + expf(-x));
+        const float ce = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+        const float q = fminf(fmaxf(pr + t - 2.0f * pr * t, 0.f), 1.0f);          // 1 - p_t
+        const float at = alpha >= 0.f ? alpha * t + (1.0f - alpha) * (1.0f - t) : 1.0f;
+        total += at * ce * powf(q, gamma);
+    }
+    loss[0] = total / (float)n;
+}
+
 // d x[b][t][pos][c] = coef[b][t*C + c] * p * c^(p-1) for x >= eps (clamp passes no gradient below eps); grid (T, b, kGemChunks)
 struct GemBwdParams {
     const __half* x; const float* coef; const float* p; __half* dx;

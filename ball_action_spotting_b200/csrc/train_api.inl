@@ -707,3 +707,12 @@ extern "C" int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* a, void* ws
 }
 
 extern "C" long long mds_train_batches_tracked(const MdsTrainer* t) { return t ? t->batches_tracked : 0; }
+
+extern "C" int mds_focal_loss(const float* logits, const float* targets, int n, float alpha, float gamma, float* loss_out,
+                              float* probs_out, void* stream) {
+    if (!logits || !targets || !loss_out || !probs_out) return fail(MDS_ERR_INVALID, "focal_loss: null argument");
+    if (n <= 0 || n > (1 << 20)) return fail(MDS_ERR_INVALID, "focal_loss: n must be in [1, 2^20]");
+    focal_loss_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, targets, n, alpha, gamma, loss_out, probs_out);
+    LAUNCH_CHECK("focal_loss");
+    return MDS_OK;
+}

@@ -44,6 +44,9 @@ class FrozenEncoderTrainer:
         cfg = model._cfg
         self.lr = float(lr)
         self.ema_decay = ema_decay        # ModelEma decay (configs: ema_decay=0.999); None = no averaging
+        self.focal_alpha, self.focal_gamma = float(focal_alpha), float(focal_gamma)
+        self._val_module: Optional[MultiDimStacker] = None
+        self._val_version = -1
         self._ema_tracked = None
         self.cfg = MdsTrainConfig(
             cfg.num_classes, cfg.num_frames, cfg.stack_size, cfg.num_3d_blocks, cfg.num_3d_features, cfg.num_3d_stack_proj,
@@ -204,3 +207,33 @@ class FrozenEncoderTrainer:
         if self.ema_decay is not None:
             self.ema_update()
         return {"prediction": torch.sigmoid(logits), "target": target, "loss": loss.item()}     # prediction_transform (:26,69)
+
+    def val_step(self, batch, state=None) -> dict:
+        """``BallActionModel.val_step(batch, state)`` (argus_models.py:76-91): eval-mode forward of the EMA model when
+        averaging is on (else of the current weights), focal loss, sigmoid.  The evaluation copy of the module is refreshed
+        only when a training step has happened since the last call."""
+        frames, target = batch
+        frames = frames.to(self.device, non_blocking=True)
+        target = target.to(self.device, torch.float32, non_blocking=True).contiguous()
+        if self._val_module is None:          # a second module (its own engine handle) holding the weights to evaluate
+            c = self.model._cfg
+            self._val_module = MultiDimStacker("tf_efficientnetv2_b0.in1k", c.num_classes, num_frames=c.num_frames,
+                                               stack_size=c.stack_size, num_3d_blocks=c.num_3d_blocks,
+                                               num_3d_features=c.num_3d_features, num_3d_stack_proj=c.num_3d_stack_proj,
+                                               expansion_3d_ratio=c.expansion_3d_ratio, se_reduce_3d_ratio=c.se_reduce_3d_ratio,
+                                               drop_rate=self.model.drop_rate, chunk_images=c.chunk_images,
+                                               bias_correction=self.model._bias_correction).to(self.device).eval()
+        if self._val_version != self._step:
+            if self.ema_decay is not None:
+                self._val_module.load_state_dict(self.ema_state_dict())
+            else:
+                self.sync_to_module()
+                self._val_module.load_state_dict(self.model.state_dict())
+            self._val_version = self._step
+        logits = self._val_module(frames).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        probs = torch.empty_like(logits)
+        check(self.lib.mds_focal_loss(logits.data_ptr(), target.data_ptr(), logits.numel(), self.focal_alpha, self.focal_gamma,
+                                      loss.data_ptr(), probs.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),
+              "mds_focal_loss")
+        return {"prediction": probs, "target": target, "loss": loss.item()}

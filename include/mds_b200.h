@@ -189,6 +189,10 @@ int mds_train_step(MdsTrainer* t, const MdsTrainStepArgs* args, void* ws, size_t
 /* host4: loss scale, growth tracker, found_inf flag, optimizer steps performed; synchronises the device */
 int mds_train_scaler_state(MdsTrainer* t, float* host4);
 long long mds_train_batches_tracked(const MdsTrainer* t);   /* BatchNorm num_batches_tracked increment */
+/* Validation step (BallActionModel.val_step, src/argus_models.py:76-91): sigmoid focal loss (src/losses.py:31-48, mean
+ * reduction) of n = b * num_classes eval-mode logits and their sigmoid (prediction_transform); device pointers. */
+int mds_focal_loss(const float* logits, const float* targets, int n, float alpha, float gamma, float* loss_out,
+                   float* probs_out, void* stream);
 
 /* ---- post-processing of raw predictions into action spots ----------------------------------------------------------
  * Replaces post_processing (src/utils.py:55-64) for every class at once: scipy.ndimage.gaussian_filter (1-D, 'reflect',

@@ -157,3 +157,32 @@ def test_model_ema_follows_the_reference_recursion():
     assert torch.equal(esd["classifier.bias"].cpu(), ema["classifier.bias"])
     assert int(esd["conv3d_encoder.0.bn1.bn3d.num_batches_tracked"]) == int(0.9 * int(0.9 * int(0.9 * 0 + 0.1 * 1) + 0.1 * 2) + 0.1 * 3)
     tr.close()
+
+
+def test_val_step_uses_ema_weights_and_matches_the_oracle_loss():
+    """BallActionModel.val_step (argus_models.py:76-91): eval forward of the EMA model, focal loss, sigmoid."""
+    from ball_action_spotting_b200 import FrozenEncoderTrainer
+    cfg = O.ModelConfig(num_frames=9)
+    sd = O.make_state_dict(cfg, seed=1234, calib_hw=(96, 160))
+    net, tr0 = TP.build(cfg, sd)
+    tr0.close()
+    tr = FrozenEncoderTrainer(net, lr=0.05, ema_decay=0.5)
+    frames = torch.randint(0, 256, (2, 9, 96, 160), dtype=torch.uint8, generator=torch.Generator().manual_seed(0))
+    target = torch.tensor([[1.0, 0.0], [0.3, 1.0]])
+    for _ in range(2):
+        tr.train_step((frames, target))
+    out = tr.val_step((frames, target))
+    # oracle: eval-mode forward with the EMA state dict, the reference's focal loss, sigmoid
+    esd = {k: v.detach().float().cpu() for k, v in tr.ema_state_dict().items()}
+    with torch.no_grad():
+        ref_logits = O.forward(esd, O.pad_normalize(frames, (160, 96)), cfg)
+    ref_loss = TO.sigmoid_focal_loss(ref_logits, target, TP.ALPHA, TP.GAMMA)
+    tol = 1e-3 * (920.0 / 15.0) ** 0.5                      # 96x160 input: 15 GeM positions (see tests/test_e2e_gpu.py)
+    assert (out["prediction"].cpu() - torch.sigmoid(ref_logits)).abs().max() <= tol
+    assert abs(out["loss"] - ref_loss.item()) <= tol * max(1.0, abs(ref_loss.item()))
+    assert out["target"].shape == (2, 2)
+    # the EMA weights differ from the current ones, and val_step evaluates the EMA ones
+    tr.sync_to_module()
+    cur = net(frames.to(DEV)).cpu()
+    assert (torch.sigmoid(cur) - out["prediction"].cpu()).abs().max() > 1e-6
+    tr.close()
