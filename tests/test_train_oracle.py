@@ -85,3 +85,53 @@ def test_train_oracle_vs_unmodified_reference_step():
     assert torch.allclose(loss, r_loss, rtol=1e-5) and torch.allclose(logits, r_logits, rtol=1e-5, atol=1e-6)
     for k in grads:
         assert torch.allclose(grads[k], r_grads[k], rtol=1e-4, atol=1e-7), k
+
+
+def test_batchnorm_silu_backward_closed_form():
+    """The algebra of bn_bwd_reduce / bn_bwd_finalize / bn_bwd_apply (csrc/train.cuh): with dz = da * silu'(z),
+    S1 = sum(dz), S2 = sum(dz * (y - mean)):  d beta = S1, d gamma = rstd * S2, and
+    dy = gr * dz + A * y + B  with gr = gamma * rstd, A = -rstd * gr * (d gamma / M), B = -gr * S1 / M - mean * A."""
+    g = torch.Generator().manual_seed(0)
+    M, C = 257, 24
+    y = (torch.randn(M, C, generator=g) * 1.3 + 0.4).double().requires_grad_(True)
+    gamma = (torch.rand(C, generator=g) + 0.5).double().requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.1).double().requires_grad_(True)
+    da = torch.randn(M, C, generator=g).double()
+    eps = 1e-5
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    z = (y - mean) * rstd * gamma + beta
+    (torch.nn.functional.silu(z) * da).sum().backward()
+    with torch.no_grad():
+        sig = torch.sigmoid(z)
+        dz = da * sig * (1 + z * (1 - sig))
+        S1, S2 = dz.sum(0), (dz * (y - mean)).sum(0)
+        dgamma = rstd * S2
+        gr = gamma * rstd
+        A = -rstd * gr * (dgamma / M)
+        B = -gr * S1 / M - mean * A
+        dy = gr * dz + A * y + B
+    assert torch.allclose(beta.grad, S1, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(gamma.grad, dgamma, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(y.grad, dy, rtol=1e-9, atol=1e-12)
+
+
+def test_gem_backward_closed_form():
+    """GeM with learnable p (multidim_stacker.py:42-45): f = m^(1/p), m = mean(c^p), c = max(x, eps);
+    df/dx_i = m^(1/p - 1) c_i^(p-1) / P  (x_i >= eps),  df/dp = f * (-ln m / p^2 + mean(c^p ln c) / (p m))
+    -- the coefficients head_grad_kernel / gem_bwd_kernel use."""
+    g = torch.Generator().manual_seed(1)
+    P = 37
+    x = (torch.rand(P, generator=g) * 2 - 0.3).double().requires_grad_(True)
+    p = torch.tensor(3.0, dtype=torch.double, requires_grad=True)
+    eps = 1e-6
+    f = x.clamp(min=eps).pow(p).mean().pow(1.0 / p)
+    f.backward()
+    with torch.no_grad():
+        c = x.clamp(min=eps)
+        m = c.pow(p).mean()
+        mlog = (c.pow(p) * c.log()).mean()
+        dx = torch.where(x >= eps, m.pow(1.0 / p - 1) * c.pow(p - 1) / P, torch.zeros_like(x))
+        dp = f * (-m.log() / p ** 2 + mlog / (p * m))
+    assert torch.allclose(x.grad, dx, rtol=1e-10, atol=1e-14)
+    assert torch.allclose(p.grad, dp, rtol=1e-10)
