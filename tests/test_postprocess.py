@@ -39,6 +39,33 @@ def test_oracle_equals_reference_utils():
         assert mod.post_processing(list(range(15, 3015)), x[:, c], **PARAMS) == PO.post_processing(list(range(15, 3015)), x[:, c], **PARAMS)
 
 
+GOLD = Path(__file__).parent / "golden" / "post_processing.npz"     # written by oracle/make_post_golden.py from src/utils.py
+GOLD_CASES = [(5000, 1), (997, 2), (40, 3)]
+
+
+@pytest.mark.parametrize("n,seed", GOLD_CASES)
+def test_oracle_matches_reference_generated_golden(n, seed):
+    g = np.load(GOLD)
+    x = PO.synthetic_raw_predictions(n, 2, seed)
+    for c in range(2):
+        idx, conf = PO.post_processing(list(range(15, 15 + n)), x[:, c], **PARAMS)
+        assert idx == g[f"idx_{n}_{seed}_{c}"].tolist()
+        assert np.asarray(conf, dtype=np.float32).tolist() == g[f"conf_{n}_{seed}_{c}"].tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed", GOLD_CASES)
+def test_cuda_post_processing_matches_reference_generated_golden(n, seed):
+    import torch
+    from ball_action_spotting_b200 import postprocess as PP
+    g = np.load(GOLD)
+    x = PO.synthetic_raw_predictions(n, 2, seed)
+    for c in range(2):
+        idx, conf = PP.post_processing(list(range(15, 15 + n)), x[:, c], **PARAMS)
+        assert idx == g[f"idx_{n}_{seed}_{c}"].tolist()
+        assert np.asarray(conf, dtype=np.float32).tolist() == g[f"conf_{n}_{seed}_{c}"].tolist()
+
+
 def test_results_spotting_document():
     from ball_action_spotting_b200 import postprocess as PP
     acts = {1: {"PASS": ([30, 1500], [0.9, 0.5]), "DRIVE": ([1499], [0.7])}, 2: {"PASS": ([25], [0.3]), "DRIVE": ([], [])}}
