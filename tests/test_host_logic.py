@@ -104,3 +104,86 @@ def test_bias_correction_is_tiny_and_data_free(oracle_sd):
         if k.endswith(".b"):
             assert (a[k] - b[k]).abs().max() < 5e-3
     assert not any(".pwl" in k and k.startswith(("b3", "b4", "b5", "c3d")) for k in changed)     # SE-gated layers are untouched
+
+
+# ---- sweep window assembly on a fake engine (CPU): the index arithmetic of SlidingSweep.predict_range --------------------
+class _FakeDesc:
+    def __init__(self, frames, img_stride, plane_stride, hflip, offset_elems):
+        self.frames, self.img_stride, self.plane_stride, self.hflip, self.offset = frames, img_stride, plane_stride, hflip, offset_elems
+
+
+class _FakeEngine:
+    """Stands in for engine.Engine: an image's 'feature' is the per-frame mean of its three planes (flipped or not, which
+    the mean ignores, so the flip branch is marked by a sign), the 3D stage is the identity and the head sums over T with
+    position weights -- enough to tell whether every prediction sees exactly the triples the reference predictor would."""
+
+    def __init__(self, hw):
+        self.hw = hw
+
+    def frames_desc(self, frames, H, W, img_stride, plane_stride, hflip=False, offset_elems=0):
+        return _FakeDesc(frames, img_stride, plane_stride, hflip, offset_elems)
+
+    def forward_2d(self, desc, n_img):
+        import torch
+        flat = desc.frames.reshape(-1).float()
+        hw = self.hw
+        out = torch.empty((n_img, 1, 1, 3))
+        for i in range(n_img):
+            for c in range(3):
+                o = desc.offset + i * desc.img_stride + c * desc.plane_stride
+                out[i, 0, 0, c] = flat[o:o + hw].mean() * (-1.0 if desc.hflip else 1.0)
+        return out
+
+    def gather_stacks(self, feats, first_image, hop, n_pred, T):
+        import torch
+        idx = first_image + torch.arange(n_pred)[:, None] + hop * torch.arange(T)[None, :]
+        return feats[idx.reshape(-1)].view(n_pred, T, *feats.shape[1:])
+
+    def forward_3d(self, x):
+        return x
+
+    def forward_head(self, x, sigmoid=False):
+        import torch
+        w = torch.arange(1, x.shape[1] * 3 + 1, dtype=torch.float32).view(1, x.shape[1], 3)
+        s = (x.reshape(x.shape[0], x.shape[1], 3) * w).sum((1, 2))
+        return torch.stack([s, -s], 1)
+
+    def axpby_(self, y, x, a, b):
+        y.mul_(a).add_(x, alpha=b)
+        return y
+
+
+class _FakeModule:
+    stack_size = 3
+
+    class _cfg:
+        num_classes = 2
+
+    def __init__(self, hw):
+        self._eng = _FakeEngine(hw)
+
+    def engine(self, device):
+        return self._eng
+
+
+@pytest.mark.parametrize("tta", [False, True])
+def test_sweep_assembles_the_same_windows_as_the_streaming_predictor(tta):
+    import torch
+    from ball_action_spotting_b200.indexes import StackIndexesGenerator
+    from ball_action_spotting_b200.sweep import SlidingSweep
+    h, w, n = 2, 4, 70
+    frames = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, generator=torch.Generator().manual_seed(0))
+    sweep = SlidingSweep(_FakeModule(h * w), 15, 2, (w, h), tta=tta, max_stacks=7)        # several ragged chunks
+    first_frame, a, b = 100, 120, 143                                                       # buffer = video frames 100..169
+    got = sweep.predict_range(frames, first_frame, a, b)
+    gen = StackIndexesGenerator(15, 2)
+    means = frames.float().mean((1, 2))
+    weights = torch.arange(1, 16, dtype=torch.float32)
+    for j, p in enumerate(range(a, b)):
+        idx = gen.make_stack_indexes(p)                                                      # predictors.py:56
+        assert idx[0] == p - 14 and idx[-1] == p + 14
+        s = (means[[i - first_frame for i in idx]] * weights).sum()
+        want = torch.stack([s, -s]) * (0.0 if tta else 1.0)       # the fake flip branch negates: the TTA mean cancels exactly
+        assert torch.allclose(got[j], want, rtol=1e-5, atol=1e-3), (p, got[j], want)
+    with pytest.raises(RuntimeError, match="need frames"):
+        sweep.predict_range(frames, first_frame, 110, 120)                                   # halo outside the buffer
