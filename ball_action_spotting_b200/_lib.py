@@ -60,6 +60,7 @@ SIGNATURES = {
     "mds_k_dwconv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mds_k_se_fc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "mds_k_gemm_gated": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mds_k_mbconv_tail": (_i, [_vp] * 15 + [_i] * 11 + [_vp]),
     "mds_k_gem": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp]),
     "mds_k_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mds_train_create": (_i, [C.POINTER(MdsTrainConfig), C.POINTER(_vp)]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "mds_post_processing_workspace_bytes": (_sz, [_i, _i]),
     "mds_post_processing": (_i, [_vp, _i, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mds_set_pdl": (_i, [_i]),
+    "mds_set_fused_tail": (_i, [_i]),
     "mds_launch_count": (C.c_longlong, [_i]),
     "mds_profile_begin": (_i, []),
     "mds_profile_end": (_i, [_vp, _vp, _vp, _i, _vp]),

@@ -14,7 +14,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def sources():
-    return sorted(CSRC.glob("*.cu")), sorted(list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "mds_b200.h"])
+    return sorted(CSRC.glob("*.cu")), sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inl")) + [PKG.parent / "include" / "mds_b200.h"])
 
 
 def is_stale() -> bool:

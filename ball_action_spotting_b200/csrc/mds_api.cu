@@ -18,6 +18,7 @@
 #include "dwconv.cuh"
 #include "gemm1x1.cuh"
 #include "gemm_tc.cuh"
+#include "mbconv_tail.cuh"
 #include "se_head.cuh"
 #include "stem.cuh"
 #include "train.cuh"
@@ -131,6 +132,9 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 extern "C" int mds_set_pdl(int enabled) { g_pdl = enabled != 0; return MDS_OK; }
+// MBConv tails: 1 = one fused launch (mbconv_tail.cuh), 0 = depthwise / SE / gated GEMM as three launches (A/B measurements)
+static bool g_fused_tail = !(getenv("MDS_FUSED_TAIL") && getenv("MDS_FUSED_TAIL")[0] == '0');
+extern "C" int mds_set_fused_tail(int enabled) { g_fused_tail = enabled != 0; return MDS_OK; }
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -453,6 +457,139 @@ static int launch_se(const float* partials, int nparts, const float* w1, const f
     return MDS_OK;
 }
 
+
+// ---- fused MBConv tail (mbconv_tail.cuh): depthwise + SE + gated projection in one persistent launch ----
+// input halo rows for the depthwise items: 4-D ([n][H][W][C]) or 5-D ([n][T][H][W][C]) map, no swizzle, zero fill
+static int make_tmap_dw(CUtensorMap* map, const void* ptr, int n, int T, int H, int W, int C, int kt, int stride) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    const cuuint32_t iw = stride == 1 ? kTlTWX + 2 : 2 * kTlTWX + 1;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r;
+    if (kt == 1) {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kTlCS, iw, 2, 1};
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)n};
+        cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)T * H * W * C * 2};
+        cuuint32_t box[5] = {(cuuint32_t)kTlCS, iw, 1, 3, 1};
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled(dw) failed (%d) n=%d T=%d H=%d W=%d C=%d", (int)r, n, T, H, W, C);
+    return MDS_OK;
+}
+
+struct TailArgs {
+    const __half* m1;        // [n][T][H][W][C] expanded input
+    __half* m2;              // [n][T][Ho][Wo][C]
+    const float *dw_w, *dw_b, *se_w1, *se_b1, *se_w2t, *se_b2;
+    float* partials;         // [n][kDwMaxParts][C]
+    float* gate;             // [n][C] f32
+    int* sync;               // [3][sync_stride] zero
+    int sync_stride;
+    const __half* wpwl;      // [N][C] fp16 (N == 0: depthwise + SE only)
+    const __half* bm;        // [N][64] bias matrix
+    const __half* res;
+    __half* out;
+    int n, T, H, W, C, kt, stride, rd, N;
+    int rows_per_chunk;      // 0: default
+    int lag;                 // 0: default
+};
+
+static int g_tail_rows = getenv("MDS_TAIL_ROWS") ? atoi(getenv("MDS_TAIL_ROWS")) : 12;
+static long long g_tail_l2_bytes = getenv("MDS_TAIL_L2_MB") ? atoll(getenv("MDS_TAIL_L2_MB")) << 20 : (24LL << 20);
+
+template <int KT, int STRIDE>
+static int launch_tail_t(const CUtensorMap& tmDw, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBias,
+                         TailParams& p, cudaStream_t st) {
+    using Cfg = TailCfg<KT, STRIDE>;
+    auto kern = mbconv_tail_kernel<KT, STRIDE>;
+    p.g_stages = 4;
+    size_t smem = tl_smem_bytes(Cfg::DW_RING, p.N, p.g_stages, KT);
+    if (smem > 227 * 1024) { p.g_stages = 3; smem = tl_smem_bytes(Cfg::DW_RING, p.N, p.g_stages, KT); }
+    if (smem > 227 * 1024) return fail(MDS_ERR_INVALID, "mbconv_tail: N=%d needs %zu bytes of shared memory", p.N, smem);
+    {
+        static size_t smem_set[kMaxDevices] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < kMaxDevices && smem > smem_set[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[dev] = smem;
+        }
+    }
+    int grid = num_sms();
+    if (p.n_items < grid) grid = p.n_items;
+    ProfScope ps(KT == 1 ? MDS_KIND_TAIL2D : MDS_KIND_TAIL3D, st);
+    launch_pdl(kern, dim3(grid), dim3(kTlThreads), smem, st, tmDw, tmA, tmB, tmBias, p);
+    LAUNCH_CHECK("mbconv_tail");
+    return MDS_OK;
+}
+
+static int launch_tail(const TailArgs& a, cudaStream_t st) {
+    if (a.n <= 0) return MDS_OK;
+    if (a.C % 8 || a.C > kTlMaxC || a.C < kTlCS) return fail(MDS_ERR_INVALID, "mbconv_tail: C must be a multiple of 8 in [128, 1152] (C=%d)", a.C);
+    if (a.rd <= 0 || a.rd > kTlMaxRd) return fail(MDS_ERR_INVALID, "mbconv_tail: rd must be in [1, 64]");
+    if (!((a.kt == 1 && (a.stride == 1 || a.stride == 2)) || (a.kt == 3 && a.stride == 1)))
+        return fail(MDS_ERR_INVALID, "mbconv_tail: unsupported kt=%d stride=%d", a.kt, a.stride);
+    if (a.kt == 1 && a.T != 1) return fail(MDS_ERR_INVALID, "mbconv_tail 2D: T must be 1");
+    if (a.stride == 2 && (a.H % 2 || a.W % 2)) return fail(MDS_ERR_INVALID, "mbconv_tail: stride-2 input must be even");
+    if (a.N && (a.N % 16 || a.N < 32 || a.N > 256)) return fail(MDS_ERR_INVALID, "mbconv_tail: N must be a multiple of 16 in [32, 256]");
+    if (a.n > a.sync_stride) return fail(MDS_ERR_INVALID, "mbconv_tail: %d images exceed the %d sync slots", a.n, a.sync_stride);
+    TailParams p;
+    memset(&p, 0, sizeof(p));
+    p.m2 = a.m2; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.partials = a.partials;
+    p.se_w1 = a.se_w1; p.se_b1 = a.se_b1; p.se_w2t = a.se_w2t; p.se_b2 = a.se_b2; p.gate = a.gate;
+    p.sync = a.sync; p.sync_stride = a.sync_stride; p.out = a.out; p.res = a.res;
+    p.n = a.n; p.T = a.T; p.H = a.H; p.W = a.W; p.C = a.C; p.Ho = a.H / a.stride; p.Wo = a.W / a.stride; p.rd = a.rd;
+    p.inv_count = 1.0f / (float)((size_t)a.T * p.Ho * p.Wo);
+    // row chunks are a function of the layer shape only, so the squeeze partial sums (and with them every logit) do not
+    // depend on what else is in the batch
+    const int want_rows = a.rows_per_chunk > 0 ? a.rows_per_chunk : g_tail_rows;
+    int chunks = (p.Ho + want_rows / 2) / want_rows;
+    if (chunks < 1) chunks = 1;
+    p.xtiles = (p.Wo + kTlTWX - 1) / kTlTWX;
+    while (chunks > 1 && (long long)chunks * a.T * p.xtiles > kDwMaxParts) --chunks;
+    p.rows_per_chunk = (p.Ho + chunks - 1) / chunks;
+    p.chunks = (p.Ho + p.rows_per_chunk - 1) / p.rows_per_chunk;
+    p.slab_pairs = (a.C + kTlCS - 1) / kTlCS;
+    p.nparts = p.chunks * a.T * p.xtiles;
+    if (p.nparts > kDwMaxParts) return fail(MDS_ERR_INVALID, "mbconv_tail: %d squeeze partials per image exceed %d", p.nparts, kDwMaxParts);
+    p.dw_per_img = a.T * p.chunks * p.xtiles * p.slab_pairs;
+    p.rows_per_img = a.T * p.Ho * p.Wo;
+    p.N = a.N;
+    p.tiles_per_img = a.N ? (p.rows_per_img + kTcBM - 1) / kTcBM : 0;
+    p.num_kb = (a.C + kTcBK - 1) / kTcBK;
+    // images per block of the item order: as many as keep ~2.5 blocks of depthwise output inside L2
+    const long long img_bytes = (long long)p.rows_per_img * a.C * 2;
+    long long lag = a.lag > 0 ? a.lag : g_tail_l2_bytes / (img_bytes > 0 ? img_bytes : 1);
+    if (lag < 2) lag = 2;
+    if (lag > a.n || a.N == 0) lag = a.n;
+    p.lag = (int)lag;
+    const long long items = (long long)a.n * (p.dw_per_img + p.tiles_per_img);
+    if (items >= (1LL << 31)) return fail(MDS_ERR_INVALID, "mbconv_tail: too many work items");
+    p.n_items = (int)items;
+    int cols = 32;
+    while (cols < 2 * (a.N ? a.N : 16)) cols <<= 1;
+    p.tmem_cols = cols;
+
+    CUtensorMap tmDw, tmA, tmB, tmBias;
+    TRY(make_tmap_dw(&tmDw, a.m1, a.n, a.T, a.H, a.W, a.C, a.kt, a.stride));
+    if (a.N) {
+        TRY(make_tmap_2d(&tmA, a.m2, (long long)a.n * p.rows_per_img, a.C, kTcBM));
+        TRY(make_tmap_2d(&tmB, a.wpwl, a.N, a.C, a.N));
+        TRY(make_tmap_2d(&tmBias, a.bm, a.N, kTcBK, a.N));
+    } else {
+        tmA = tmDw; tmB = tmDw; tmBias = tmDw;      // never dereferenced
+    }
+    if (a.kt == 3) return launch_tail_t<3, 1>(tmDw, tmA, tmB, tmBias, p, st);
+    if (a.stride == 1) return launch_tail_t<1, 1>(tmDw, tmA, tmB, tmBias, p, st);
+    return launch_tail_t<1, 2>(tmDw, tmA, tmB, tmBias, p, st);
+}
+
 static size_t gem_part_floats(int b, int T, int C) { return (size_t)b * T * kGemSplit * C; }
 static int launch_gem(const __half* x, float* feat, float* part, int b, int T, int P, int C, float pw, float eps, cudaStream_t st) {
     if (C % 8 || C > 256 || C < 32) return fail(MDS_ERR_INVALID, "gem: C must be a multiple of 8 in [32, 256]");
@@ -511,6 +648,7 @@ struct MdsHandle {
     std::vector<Block3d> blocks3d;
     float gem_p = 3.0f;
     const float *cls_w = nullptr, *cls_b = nullptr;
+    int* sync = nullptr;          // [3][kSyncSlots] inter-CTA words of the fused MBConv tail; zero between launches
     int T() const { return cfg.num_frames / cfg.stack_size; }
     int mid3d() const { return cfg.num_3d_features * cfg.expansion_3d_ratio; }
     int rd3d() const { return mid3d() / cfg.se_reduce_3d_ratio; }
@@ -526,6 +664,7 @@ struct DeviceGuard {
     ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
 };
 
+constexpr int kSyncSlots = 4096;      // images per pass of the fused MBConv tail (>= chunk_images)
 static const int kStageDefs[6][6] = {
     // kind(0 c,1 e,2 i), repeats, stride, expand, cout, se (x100)
     {0, 1, 1, 1, 16, 0}, {1, 2, 2, 4, 32, 0}, {1, 2, 2, 4, 48, 0}, {2, 3, 2, 4, 96, 25}, {2, 5, 1, 6, 112, 25}, {2, 8, 2, 6, 192, 25}};
@@ -548,6 +687,13 @@ extern "C" int mds_create(const MdsConfig* cfg, MdsHandle** out) {
     MdsHandle* h = new MdsHandle();
     h->cfg = *cfg;
     if (h->cfg.chunk_images <= 0) h->cfg.chunk_images = 160;   // one pass for up to 32 stacks; ~41 MB of scratch per image
+    if (h->cfg.chunk_images > kSyncSlots) h->cfg.chunk_images = kSyncSlots;
+    {
+        DeviceGuard g(cfg->device);
+        cudaError_t e = cudaMalloc(&h->sync, 3 * kSyncSlots * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(h->sync, 0, 3 * kSyncSlots * sizeof(int));
+        if (e != cudaSuccess) { delete h; return fail(MDS_ERR_CUDA, "mds_create: %s", cudaGetErrorString(e)); }
+    }
     *out = h;
     return MDS_OK;
 }
@@ -556,6 +702,7 @@ extern "C" int mds_destroy(MdsHandle* h) {
     if (!h) return MDS_OK;
     DeviceGuard g(h->cfg.device);
     for (auto& kv : h->tensors) cudaFree(kv.second.ptr);
+    cudaFree(h->sync);
     delete h;
     return MDS_OK;
 }
@@ -715,12 +862,13 @@ static size_t ws2d_bytes(const MdsHandle* h, int H, int W, int n_images) {
     if (cs <= 0) cs = 1;
     Sizes2d s = sizes2d(H, W);
     return 2 * al256(s.stream_elems * cs * 2) + al256(s.mid1_elems * cs * 2) + al256(s.mid2_elems * cs * 2) +
-           al256((size_t)cs * kDwMaxParts * 1152 * 4) + al256((size_t)cs * 1152 * 2) + al256((size_t)cs * kMaxGatedW * 2);
+           al256((size_t)cs * kDwMaxParts * 1152 * 4) + al256((size_t)cs * 1152 * 2) + al256((size_t)cs * 1152 * 4) +
+           al256((size_t)cs * kMaxGatedW * 2);
 }
 static size_t ws3d_bytes(const MdsHandle* h, int b, int P) {
     const size_t rows = (size_t)b * h->T() * P;
     return 2 * al256(rows * h->cfg.num_3d_features * 2) + 2 * al256(rows * h->mid3d() * 2) +
-           al256((size_t)b * kDwMaxParts * h->mid3d() * 4) + al256((size_t)b * h->mid3d() * 2) +
+           al256((size_t)b * kDwMaxParts * h->mid3d() * 4) + al256((size_t)b * h->mid3d() * 2) + al256((size_t)b * h->mid3d() * 4) +
            al256((size_t)b * h->cfg.num_3d_features * h->mid3d() * 2);
 }
 static size_t wshead_bytes(const MdsHandle* h, int b) {
@@ -761,6 +909,7 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
     __half* M2 = ar.take<__half>(sz.mid2_elems * cs_max);
     float* partials = ar.take<float>((size_t)cs_max * kDwMaxParts * 1152);
     __half* gate = ar.take<__half>((size_t)cs_max * 1152);
+    float* gate32 = ar.take<float>((size_t)cs_max * 1152);
     __half* wg = ar.take<__half>((size_t)cs_max * kMaxGatedW);
     if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_2d: workspace too small");
 
@@ -783,11 +932,21 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
                 TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, b.w2, b.b2, cs, hh, ww, b.cin, b.mid, b.stride, b.cout, b.skip, st));
             } else {
                 TRY(launch_gemm(X[cur], b.wpw, b.bpw, nullptr, nullptr, M1, (long long)hh * ww, cs, b.mid, b.cin, 1, st, b.bmpw));
-                int nparts = 0;
-                TRY(launch_dw(M1, M2, b.wdw, b.bdw, partials, &nparts, cs, 1, hh, ww, b.mid, 1, b.stride, st));
-                TRY(launch_se(partials, nparts, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, b.w32pwl, wg, cs, b.mid, b.rd, b.cout,
-                              1.0f / (float)(ho * wo), st));
-                TRY(launch_gemm_tc_stream(M2, wg, b.bmpwl, b.skip ? X[cur] : nullptr, X[cur ^ 1], ho * wo, cs, b.cout, b.mid, 0, st));
+                if (g_fused_tail) {
+                    TailArgs a;
+                    a.m1 = M1; a.m2 = M2; a.dw_w = b.wdw; a.dw_b = b.bdw; a.se_w1 = b.se_w1; a.se_b1 = b.se_b1; a.se_w2t = b.se_w2t;
+                    a.se_b2 = b.se_b2; a.partials = partials; a.gate = gate32; a.sync = h->sync; a.sync_stride = kSyncSlots;
+                    a.wpwl = b.wpwl; a.bm = b.bmpwl; a.res = b.skip ? X[cur] : nullptr; a.out = X[cur ^ 1];
+                    a.n = cs; a.T = 1; a.H = hh; a.W = ww; a.C = b.mid; a.kt = 1; a.stride = b.stride; a.rd = b.rd; a.N = b.cout;
+                    a.rows_per_chunk = 0; a.lag = 0;
+                    TRY(launch_tail(a, st));
+                } else {
+                    int nparts = 0;
+                    TRY(launch_dw(M1, M2, b.wdw, b.bdw, partials, &nparts, cs, 1, hh, ww, b.mid, 1, b.stride, st));
+                    TRY(launch_se(partials, nparts, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, b.w32pwl, wg, cs, b.mid, b.rd, b.cout,
+                                  1.0f / (float)(ho * wo), st));
+                    TRY(launch_gemm_tc_stream(M2, wg, b.bmpwl, b.skip ? X[cur] : nullptr, X[cur ^ 1], ho * wo, cs, b.cout, b.mid, 0, st));
+                }
             }
             cur ^= 1; hh = ho; ww = wo;
         }
@@ -816,6 +975,7 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
     __half* M2 = ar.take<__half>(rows * mid);
     float* partials = ar.take<float>((size_t)b * kDwMaxParts * mid);
     __half* gate = ar.take<__half>((size_t)b * mid);
+    float* gate32 = ar.take<float>((size_t)b * mid);
     __half* wg = ar.take<__half>((size_t)b * c3 * mid);
     if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward_3d: workspace too small");
 
@@ -827,11 +987,21 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
     for (const Block3d& blk : h->blocks3d) {
         ++g_prof_tag;
         TRY(launch_gemm(x, blk.wpw, blk.bpw, nullptr, nullptr, M1, (long long)T * P, b, mid, c3, 1, st, blk.bmpw));
-        int nparts = 0;
-        TRY(launch_dw(M1, M2, blk.wdw, blk.bdw, partials, &nparts, b, T, fh, fw, mid, 3, 1, st));
-        TRY(launch_se(partials, nparts, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, blk.w32pwl, wg, b, mid, rd, c3,
-                      1.0f / (float)((size_t)T * P), st));
-        TRY(launch_gemm_tc_stream(M2, wg, blk.bmpwl, x, Y[nxt], T * P, b, c3, mid, 0, st));
+        if (g_fused_tail && b <= kSyncSlots) {
+            TailArgs a;
+            a.m1 = M1; a.m2 = M2; a.dw_w = blk.wdw; a.dw_b = blk.bdw; a.se_w1 = blk.se_w1; a.se_b1 = blk.se_b1; a.se_w2t = blk.se_w2t;
+            a.se_b2 = blk.se_b2; a.partials = partials; a.gate = gate32; a.sync = h->sync; a.sync_stride = kSyncSlots;
+            a.wpwl = blk.wpwl; a.bm = blk.bmpwl; a.res = x; a.out = Y[nxt];
+            a.n = b; a.T = T; a.H = fh; a.W = fw; a.C = mid; a.kt = 3; a.stride = 1; a.rd = rd; a.N = c3;
+            a.rows_per_chunk = 0; a.lag = 0;
+            TRY(launch_tail(a, st));
+        } else {
+            int nparts = 0;
+            TRY(launch_dw(M1, M2, blk.wdw, blk.bdw, partials, &nparts, b, T, fh, fw, mid, 3, 1, st));
+            TRY(launch_se(partials, nparts, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, blk.w32pwl, wg, b, mid, rd, c3,
+                          1.0f / (float)((size_t)T * P), st));
+            TRY(launch_gemm_tc_stream(M2, wg, blk.bmpwl, x, Y[nxt], T * P, b, c3, mid, 0, st));
+        }
         x = Y[nxt];
         nxt ^= 1;
     }
@@ -984,6 +1154,22 @@ extern "C" int mds_k_gemm_gated(const void* A, const void* wg, const void* bias_
     return launch_gemm_tc_stream(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(wg),
                                  reinterpret_cast<const __half*>(bias_mat), reinterpret_cast<const __half*>(res),
                                  reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_mbconv_tail(const void* m1, void* m2, const float* dw_w, const float* dw_b, float* partials, const float* se_w1,
+                                 const float* se_b1, const float* se_w2t, const float* se_b2, float* gate, int* sync, const void* wpwl,
+                                 const void* bias_mat, const void* res, void* out, int n, int T, int H, int W, int C, int kt, int stride,
+                                 int rd, int N, int rows_per_chunk, int lag, void* stream) {
+    if (!m1 || !m2 || !dw_w || !dw_b || !partials || !se_w1 || !se_b1 || !se_w2t || !se_b2 || !gate || !sync)
+        return fail(MDS_ERR_INVALID, "mbconv_tail: null argument");
+    if (N && (!wpwl || !bias_mat || !out)) return fail(MDS_ERR_INVALID, "mbconv_tail: null projection argument");
+    TailArgs a;
+    a.m1 = reinterpret_cast<const __half*>(m1); a.m2 = reinterpret_cast<__half*>(m2); a.dw_w = dw_w; a.dw_b = dw_b;
+    a.se_w1 = se_w1; a.se_b1 = se_b1; a.se_w2t = se_w2t; a.se_b2 = se_b2; a.partials = partials; a.gate = gate;
+    a.sync = sync; a.sync_stride = n; a.wpwl = reinterpret_cast<const __half*>(wpwl); a.bm = reinterpret_cast<const __half*>(bias_mat);
+    a.res = reinterpret_cast<const __half*>(res); a.out = reinterpret_cast<__half*>(out);
+    a.n = n; a.T = T; a.H = H; a.W = W; a.C = C; a.kt = kt; a.stride = stride; a.rd = rd; a.N = N;
+    a.rows_per_chunk = rows_per_chunk; a.lag = lag;
+    return launch_tail(a, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int mds_k_gem(const void* x, float* feat, int b, int T, int P, int C, float p, float eps, void* stream) {
     // per-kernel entry point (tests): the slice sums need scratch, allocated here stream-ordered

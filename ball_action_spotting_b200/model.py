@@ -101,6 +101,7 @@ class MultiDimStacker(nn.Module):
         self.num_stacks = num_frames // stack_size
         self.num_features = num_3d_stack_proj * self.num_stacks
         self.drop_rate = drop_rate
+        self.drop_path_rate = drop_path_rate      # used by train.FrozenEncoderTrainer (DropPath of the 3D blocks, :122)
         mid = num_3d_features * expansion_3d_ratio
         self._cfg = EngineConfig(num_classes, num_frames, stack_size, num_3d_blocks, num_3d_features, num_3d_stack_proj,
                                  expansion_3d_ratio, se_reduce_3d_ratio, chunk_images)

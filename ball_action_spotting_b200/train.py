@@ -33,7 +33,7 @@ class FrozenEncoderTrainer:
 
     def __init__(self, model: MultiDimStacker, lr: float, momentum: float = 0.9, nesterov: bool = True,
                  focal_alpha: float = 0.4, focal_gamma: float = 1.2, amp: bool = True,
-                 drop_rate: Optional[float] = None, drop_path_rate: float = 0.2, init_scale: float = 65536.0,
+                 drop_rate: Optional[float] = None, drop_path_rate: Optional[float] = None, init_scale: float = 65536.0,
                  ema_decay: Optional[float] = None):
         self.lib = _lib.load()
         self.model = model
@@ -51,7 +51,8 @@ class FrozenEncoderTrainer:
         self.cfg = MdsTrainConfig(
             cfg.num_classes, cfg.num_frames, cfg.stack_size, cfg.num_3d_blocks, cfg.num_3d_features, cfg.num_3d_stack_proj,
             cfg.expansion_3d_ratio, cfg.se_reduce_3d_ratio, self.device.index, 1 if amp else 0, 1 if nesterov else 0,
-            float(model.drop_rate if drop_rate is None else drop_rate), float(drop_path_rate), float(focal_alpha),
+            float(model.drop_rate if drop_rate is None else drop_rate),
+            float(model.drop_path_rate if drop_path_rate is None else drop_path_rate), float(focal_alpha),
             float(focal_gamma), float(momentum), float(init_scale))
         h = C.c_void_p()
         check(self.lib.mds_train_create(C.byref(self.cfg), C.byref(h)), "mds_train_create")

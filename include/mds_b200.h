@@ -7,7 +7,8 @@
  * a parameter says "host"; no torch types cross this boundary.  Every function returns 0 on success and a
  * negative MdsStatus on failure; mds_last_error() returns a thread-local message.  Launches are asynchronous
  * on the caller's stream (the reference runs on the current stream without syncs, src/predictors.py:50).
- * Ownership: the caller owns every input/output/workspace buffer; the handle owns only packed weights.
+ * Ownership: the caller owns every input/output/workspace buffer; the handle owns only packed weights and a few KB of
+ * inter-CTA synchronisation words.
  * A handle is bound to one device and is not thread-safe (the reference is single-threaded per device).
  */
 #ifndef MDS_B200_H_
@@ -125,6 +126,16 @@ int mds_k_se_fc(const float* partials, int nparts, const float* w1, const float*
 /* SE-gated projection GEMM on tcgen05: C[img] = act(A[img] . wg[img]^T + bias) (+ res); N <= 256. */
 int mds_k_gemm_gated(const void* A, const void* wg, const void* bias_mat, const void* res, void* C, int rows_per_img,
                      int n_img, int N, int K, int act, void* stream);
+/* Fused MBConv tail, ONE launch (timm InvertedResidual conv_dw/bn2/se/conv_pwl/bn3 (+ shortcut), built at
+ * multidim_stacker.py:166-176; InvertedResidual3d multidim_stacker.py:110-134): m1 fp16 [n][T][H][W][C] (expanded input) ->
+ * m2 fp16 [n][T][H/s][W/s][C] (depthwise + BN + SiLU, before gating), gate f32 [n][C] (SE excitation, SqueezeExcite :72-90),
+ * out fp16 [n][T*(H/s)*(W/s)][N] = (m2 * gate) . wpwl^T + bias (+ res).  kt = 1 (2D, stride 1 or 2, T = 1) or 3 (3x3x3).
+ * partials: f32 scratch [n][64][C]; sync: int scratch [3][n], must be ZERO on entry and is left zero (N > 0).
+ * N = 0: depthwise + SE only (wpwl / bias_mat / res / out unused; sync is left non-zero).  rows_per_chunk / lag: 0 = default. */
+int mds_k_mbconv_tail(const void* m1, void* m2, const float* dw_w, const float* dw_b, float* partials, const float* se_w1,
+                      const float* se_b1, const float* se_w2t, const float* se_b2, float* gate, int* sync, const void* wpwl,
+                      const void* bias_mat, const void* res, void* out, int n, int T, int H, int W, int C, int kt, int stride,
+                      int rd, int N, int rows_per_chunk, int lag, void* stream);
 int mds_k_gem(const void* x, float* feat, int b, int T, int P, int C, float p, float eps, void* stream);
 int mds_k_linear(const float* feat, const float* w, const float* bias, float* out, int b, int F, int num_classes,
                  int apply_sigmoid, void* stream);
@@ -137,7 +148,9 @@ typedef enum MdsKernelKind {
     MDS_KIND_STEM = 0, MDS_KIND_CONV3X3 = 1, MDS_KIND_GEMM1X1 = 2, MDS_KIND_DWCONV2D = 3, MDS_KIND_DWCONV3D = 4,
     MDS_KIND_SE_FC = 5, MDS_KIND_HEAD = 6,
     /* training step: weight-gradient GEMMs, BatchNorm column kernels, depthwise 3x3x3 fwd/bwd, small kernels */
-    MDS_KIND_TRAIN_WGRAD = 7, MDS_KIND_TRAIN_BN = 8, MDS_KIND_TRAIN_DW = 9, MDS_KIND_TRAIN_SMALL = 10
+    MDS_KIND_TRAIN_WGRAD = 7, MDS_KIND_TRAIN_BN = 8, MDS_KIND_TRAIN_DW = 9, MDS_KIND_TRAIN_SMALL = 10,
+    /* fused MBConv tail (depthwise + SE + gated projection in one launch), 2D blocks / 3D blocks */
+    MDS_KIND_TAIL2D = 11, MDS_KIND_TAIL3D = 12
 } MdsKernelKind;
 int mds_profile_begin(void);
 int mds_profile_end(int* kinds, int* tags, float* ms, int capacity, int* count);
@@ -208,6 +221,8 @@ int mds_post_processing(const float* raw, int n_frames, int num_classes, const d
 /* Programmatic dependent launch of the forward chain (default on): each kernel's launch latency, CTA scheduling and
  * constant set-up overlap the previous kernel's tail.  0 restores plain stream serialization (A/B measurements). */
 int mds_set_pdl(int enabled);
+/* MBConv tails as one fused launch (default 1, mds_k_mbconv_tail) or as depthwise / SE / gated-GEMM launches (0; A/B runs). */
+int mds_set_fused_tail(int enabled);
 
 /* number of kernels launched by this library in the calling thread since the last reset (bench "gpu_launches") */
 long long mds_launch_count(int reset);
