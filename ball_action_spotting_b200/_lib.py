@@ -60,7 +60,9 @@ SIGNATURES = {
     "mds_k_dwconv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mds_k_se_fc": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "mds_k_gemm_gated": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "mds_k_mbconv_tail": (_i, [_vp] * 15 + [_i] * 11 + [_vp]),
+    "mds_k_dwconv_se": (_i, [_vp] * 12 + [_i] * 9 + [_vp]),
+    "mds_k_gemm_gate": (_i, [_vp] * 6 + [_i] * 5 + [_vp]),
+    "mds_k_mbconv_tail": (_i, [_vp] * 15 + [_i] * 10 + [_vp]),
     "mds_k_gem": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _vp]),
     "mds_k_linear": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mds_train_create": (_i, [C.POINTER(MdsTrainConfig), C.POINTER(_vp)]),
@@ -79,7 +81,8 @@ SIGNATURES = {
     "mds_post_processing_workspace_bytes": (_sz, [_i, _i]),
     "mds_post_processing": (_i, [_vp, _i, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mds_set_pdl": (_i, [_i]),
-    "mds_set_fused_tail": (_i, [_i]),
+    "mds_set_tail_mode": (_i, [_i]),
+    "mds_set_tail_dw_only": (_i, [_i]),
     "mds_launch_count": (C.c_longlong, [_i]),
     "mds_profile_begin": (_i, []),
     "mds_profile_end": (_i, [_vp, _vp, _vp, _i, _vp]),

@@ -32,7 +32,10 @@ struct TcGemmParams {
     int stages;           // ring depth
     int tmem_cols;        // power of two >= 2*BN
     int streamed;         // 0: A row tile resident in smem, swept over all N tiles (K <= 192)
-                          // 1: A streamed with B through the ring (any K), one N tile, B = per-image gated weights
+                          // 1: A streamed with B through the ring (any K), one N tile
+    const float* gate;    // streamed mode: nullptr -> B = per-image pre-gated weights (3-D map);
+                          // else [n_img][K] fp32 SE gates: B = the shared weights (2-D map) and warps 10-17 multiply every A
+                          // block by the image's gate in shared memory (fp32 product, one rounding) before the MMAs read it
 };
 
 constexpr int kTcBM = 128, kTcBK = 64, kTcMaxKB = 3;
@@ -40,12 +43,13 @@ constexpr int kTcEpiWarps = 16;
 constexpr int kGP = 3;                 // 16-column groups an epilogue warp holds in registers at once
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 constexpr int kTcABytes = kTcBM * kTcBK * 2;          // 16 KB per K block
+constexpr int kTcMaxGateK = 1152;                     // largest gated K (blocks.5.x conv_pwl)
 
 __host__ __device__ inline int tc_stages(int BN, int streamed) { return streamed ? 4 : (BN > 192 ? 3 : 4); }
 __host__ __device__ inline size_t tc_smem_bytes(int BN, int streamed) {
     const size_t ring = streamed ? (size_t)tc_stages(BN, 1) * (kTcABytes + (size_t)BN * 128)
                                  : (size_t)2 * kTcMaxKB * kTcABytes + (size_t)tc_stages(BN, 0) * BN * 128;
-    return 1024 /*align slack*/ + kTcABytes /*ones tile*/ + ring + 256 /*barriers*/;
+    return 1024 /*align slack*/ + kTcABytes /*ones tile*/ + ring + 256 /*barriers*/ + (streamed ? kTcMaxGateK * 4 : 0) /*gate vector*/;
 }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------
@@ -153,16 +157,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* acc_full = bars + 12;           // [2]
     uint64_t* acc_empty = bars + 14;          // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* a_gated = bars + 17;            // [4]  gated mode: A block of the stage has been multiplied by the gate
+    uint32_t* s_gate_hi = reinterpret_cast<uint32_t*>(bars + 32);      // [kTcMaxGateK / 2] half2 (streamed mode)
+    uint32_t* s_gate_lo = s_gate_hi + kTcMaxGateK / 2;
+    const bool gated = p.streamed && p.gate != nullptr;
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + kTcBK - 1) / kTcBK;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&a_gated[i], kTcEpiWarps / 2); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kTcEpiWarps / 2);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], gated ? kTcEpiWarps / 4 : kTcEpiWarps / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -174,6 +182,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = i >> 3, ch = i & 7;
         reinterpret_cast<uint4*>(s_ones)[i] = (ch == (r & 7)) ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     }
+    if (gated)
+        for (int i = threadIdx.x; i < kTcMaxGateK; i += kTcThreads) s_gate_hi[i] = 0u;      // (hi and lo) entries beyond K stay zero
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -200,7 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (kb < num_kb) {
                             mbar_expect_tx(&b_full[stage], (uint32_t)(kTcABytes + b_bytes));
                             tma_load_2d(st, &tmA, &b_full[stage], kb * kTcBK, row0);
-                            tma_load_3d(st + b_off, &tmB, &b_full[stage], kb * kTcBK, 0, img);
+                            if (gated) tma_load_2d(st + b_off, &tmB, &b_full[stage], kb * kTcBK, 0);
+                            else tma_load_3d(st + b_off, &tmB, &b_full[stage], kb * kTcBK, 0, img);
                         } else {
                             mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
                             tma_load_2d(st + b_off, &tmBias, &b_full[stage], 0, 0);
@@ -248,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                     for (int kb = 0; kb <= num_kb; ++kb) {
-                        mbar_wait(&b_full[stage], phase);
+                        mbar_wait(gated ? &a_gated[stage] : &b_full[stage], phase);
                         tc_fence_after();
                         const bool bias_blk = kb == num_kb;
                         unsigned char* st = s_ring + (size_t)stage * stage_bytes;
@@ -266,14 +277,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!p.streamed) tc_commit(&a_empty[ab]);            // every MMA that reads this A tile has been issued
             }
         }
+    } else if (gated && warp >= 2 + kTcEpiWarps / 2) {
+        // ================= gaters (warps 10..17, gated mode): A block *= gate[img], in place =================
+        // 128 rows x 8 chunks of 16 B, 128-byte swizzle: thread -> physical chunk pc = gt & 7 of rows (gt >> 3) + 32 i; the
+        // logical chunk j = pc ^ (row & 7) is the same for all four rows (32 i keeps row & 7)
+        const int gt = threadIdx.x - 32 * (2 + kTcEpiWarps / 2);       // 0..255
+        int stage = 0;
+        uint32_t phase = 0;
+        int gate_img = -1;
+        for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+            const int img = mt / p.tiles_per_img;
+            asm volatile("bar.sync 1, 256;" ::: "memory");             // all gaters are done with the previous tile's gate vector
+            if (img != gate_img) {
+                // the gate is split into an fp16 (hi, lo) pair so that a * g = a * hi + a * lo runs on the packed fp16 pipe
+                // (HMUL2 + HFMA2 per two channels) and still carries the gate to ~22 bits
+                gate_img = img;
+                const float* gsrc = p.gate + (size_t)img * p.K;
+                for (int i = gt; i < (p.K >> 1); i += 256) {
+                    const float2 g = __ldg(reinterpret_cast<const float2*>(gsrc) + i);
+                    const __half2 hi = __floats2half2_rn(g.x, g.y);
+                    const float2 hf = __half22float2(hi);
+                    const __half2 lo = __floats2half2_rn(g.x - hf.x, g.y - hf.y);
+                    s_gate_hi[i] = *reinterpret_cast<const uint32_t*>(&hi);
+                    s_gate_lo[i] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            for (int kb = 0; kb <= num_kb; ++kb) {       // block num_kb = bias block: nothing to gate, but every use of a stage
+                                                         // completes one phase of each of its barriers
+                mbar_wait(&b_full[stage], phase);
+                if (kb < num_kb) {
+                    unsigned char* a_blk = s_ring + (size_t)stage * stage_bytes;
+                    const int pc = gt & 7, r0 = gt >> 3;
+                    const int j = pc ^ (r0 & 7);
+                    const uint4 gh = *reinterpret_cast<const uint4*>(s_gate_hi + kb * (kTcBK / 2) + j * 4);
+                    const uint4 gl = *reinterpret_cast<const uint4*>(s_gate_lo + kb * (kTcBK / 2) + j * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4* q = reinterpret_cast<uint4*>(a_blk + (size_t)(r0 + 32 * i) * 128 + pc * 16);
+                        uint4 v = *q;
+                        v.x = hfma2_u32(v.x, gl.x, hmul2_u32(v.x, gh.x));
+                        v.y = hfma2_u32(v.y, gl.y, hmul2_u32(v.y, gh.y));
+                        v.z = hfma2_u32(v.z, gl.z, hmul2_u32(v.z, gh.z));
+                        v.w = hfma2_u32(v.w, gl.w, hmul2_u32(v.w, gh.w));
+                        *q = v;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_gated[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
     } else {
-        // ================= epilogue (warps 2..17) =================
+        // ================= epilogue (warps 2..17; gated mode: warps 2..9) =================
         // Two groups of 8 warps; group e drains accumulator e (tiles t with t % 2 == e), so the TMEM reads and stores of
         // one tile overlap the bias/SiLU math of the other.  TMEM lane quadrant = warp % 4; the two warps of a group
         // that share a quadrant take alternate 16-column groups.
         const int q = warp & 3;
         const int e = ((warp - 2) >> 2) & 1;
-        const int half = (warp - 2) >> 3;
+        const int half = (warp - 2) >> 3;              // 0 in gated mode (8 epilogue warps: one per quadrant and accumulator)
+        const int nhalf = gated ? 1 : 2;
         const int ngroups = p.BN >> 4;
         int t = 0;
         for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
@@ -294,12 +358,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if ((t & 1) != e) continue;
                 const int n0 = nt * p.BN;
                 const bool has_res = p.res != nullptr;
-                for (int g0 = half; g0 < ngroups; g0 += 2 * kGP) {   // up to kGP column groups (48 accumulator columns) per pass
+                for (int g0 = half; g0 < ngroups; g0 += nhalf * kGP) {   // up to kGP column groups (48 accumulator columns) per pass
                     uint32_t rv[kGP][8];
                     if (has_res) {       // residual loads are issued before waiting for the accumulator
 #pragma unroll
                         for (int j = 0; j < kGP; ++j) {
-                            const int g = g0 + 2 * j;
+                            const int g = g0 + nhalf * j;
                             if (g < ngroups && row_ok) ld_global_v8(r_row + n0 + g * 16, rv[j]);
                         }
                     }
@@ -311,11 +375,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t v[kGP][16];
 #pragma unroll
                     for (int j = 0; j < kGP; ++j) {
-                        const int g = g0 + 2 * j;
+                        const int g = g0 + nhalf * j;
                         if (g < ngroups) tc_ld16(t_row + (uint32_t)(g * 16), v[j]);
                     }
                     tc_wait_ld();
-                    if (g0 + 2 * kGP >= ngroups) {
+                    if (g0 + nhalf * kGP >= ngroups) {
                         // last TMEM read of this tile: hand the accumulator back before doing the math / stores
                         tc_fence_before();
                         __syncwarp();
@@ -323,7 +387,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
 #pragma unroll
                     for (int j = 0; j < kGP; ++j) {
-                        const int g = g0 + 2 * j;
+                        const int g = g0 + nhalf * j;
                         if (g < ngroups) {
                             uint32_t pk[8];
 #pragma unroll

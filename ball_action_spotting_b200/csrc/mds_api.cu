@@ -16,6 +16,7 @@
 #include "conv3x3.cuh"
 #include "conv3x3_tc.cuh"
 #include "dwconv.cuh"
+#include "dwconv_tma.cuh"
 #include "gemm1x1.cuh"
 #include "gemm_tc.cuh"
 #include "mbconv_tail.cuh"
@@ -132,9 +133,21 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 extern "C" int mds_set_pdl(int enabled) { g_pdl = enabled != 0; return MDS_OK; }
-// MBConv tails: 1 = one fused launch (mbconv_tail.cuh), 0 = depthwise / SE / gated GEMM as three launches (A/B measurements)
-static bool g_fused_tail = !(getenv("MDS_FUSED_TAIL") && getenv("MDS_FUSED_TAIL")[0] == '0');
-extern "C" int mds_set_fused_tail(int enabled) { g_fused_tail = enabled != 0; return MDS_OK; }
+// MBConv tails (depthwise + SE + projection), selectable for A/B measurements (profiles/experiments_r02.md):
+//   3 (default): dwconv_tma_kernel (TMA-staged depthwise + squeeze partials), se_fc_kernel (excitation + per-image gated
+//                projection weights), tcgen05 GEMM on the pre-gated weights                               -> 3 launches
+//   2: dwconv_tma_kernel incl. the SE MLP (last CTA of an image), tcgen05 GEMM gating its A operand in smem -> 2 launches
+//   1: mbconv_tail_kernel, everything in ONE persistent launch (depthwise and projection streams on disjoint warps)
+//   0: round-1 path: cp.async depthwise kernel (batch-dependent row chunks), se_fc_kernel, GEMM            -> 3 launches
+static int g_tail_mode = getenv("MDS_TAIL_MODE") ? atoi(getenv("MDS_TAIL_MODE")) : 3;
+extern "C" int mds_set_tail_mode(int mode) {
+    if (mode < 0 || mode > 3) return fail(MDS_ERR_INVALID, "tail mode must be 0..3");
+    g_tail_mode = mode;
+    return MDS_OK;
+}
+// measurement only (bench.py roofline_dw): 1 = the fused tails run their depthwise + SE items alone (outputs are NOT valid)
+static bool g_tail_dw_only = false;
+extern "C" int mds_set_tail_dw_only(int enabled) { g_tail_dw_only = enabled != 0; return MDS_OK; }
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -335,7 +348,7 @@ static int launch_gemm_tc(const __half* A, const __half* W, const __half* bias_m
     TRY(make_tmap_2d(&tmBias, bias_mat, N, kTcBK, BN));
     TcGemmParams p;
     p.C = C; p.res = nullptr; p.M = M; p.rows_per_img = (int)M; p.tiles_per_img = (int)((M + kTcBM - 1) / kTcBM);
-    p.N = N; p.K = K; p.BN = BN; p.act = act; p.streamed = 0;
+    p.N = N; p.K = K; p.BN = BN; p.act = act; p.streamed = 0; p.gate = nullptr;
     p.m_tiles = p.tiles_per_img;
     p.n_tiles = N / BN;
     return tc_launch(tmA, tmB, tmBias, p, st);
@@ -343,18 +356,23 @@ static int launch_gemm_tc(const __half* A, const __half* W, const __half* bias_m
 
 // streamed mode: C[img] = act(A[img] Wg[img]^T + bias) (+ res); Wg = per-image SE-gated weights written by se_fc_kernel
 static int launch_gemm_tc_stream(const __half* A, const __half* Wg, const __half* bias_mat, const __half* res, __half* C,
-                                 int rows_per_img, int n_img, int N, int K, int act, cudaStream_t st) {
+                                 int rows_per_img, int n_img, int N, int K, int act, cudaStream_t st, const float* gate = nullptr) {
     if (N < 32 || N > 256 || N % 16 || K % 16) return fail(MDS_ERR_INVALID, "gemm_tc_stream: unsupported N=%d K=%d", N, K);
     if (rows_per_img <= 0 || n_img <= 0) return MDS_OK;
     const long long M = (long long)rows_per_img * n_img;
     if (M >= (1LL << 31)) return fail(MDS_ERR_INVALID, "gemm_tc_stream: too many rows");
     CUtensorMap tmA, tmB, tmBias;
     TRY(make_tmap_2d(&tmA, A, M, K, kTcBM));
-    TRY(make_tmap_3d(&tmB, Wg, n_img, N, K, N));
+    if (gate) {       // Wg = the shared [N][K] weights; the kernel applies gate[img] to the A blocks
+        if (K > kTcMaxGateK) return fail(MDS_ERR_INVALID, "gemm_tc_stream: gated K=%d exceeds %d", K, kTcMaxGateK);
+        TRY(make_tmap_2d(&tmB, Wg, N, K, N));
+    } else {
+        TRY(make_tmap_3d(&tmB, Wg, n_img, N, K, N));
+    }
     TRY(make_tmap_2d(&tmBias, bias_mat, N, kTcBK, N));
     TcGemmParams p;
     p.C = C; p.res = res; p.M = M; p.rows_per_img = rows_per_img; p.tiles_per_img = (rows_per_img + kTcBM - 1) / kTcBM;
-    p.N = N; p.K = K; p.BN = N; p.act = act; p.streamed = 1;
+    p.N = N; p.K = K; p.BN = N; p.act = act; p.streamed = 1; p.gate = gate;
     p.m_tiles = p.tiles_per_img * n_img;
     p.n_tiles = 1;
     return tc_launch(tmA, tmB, tmBias, p, st);
@@ -469,7 +487,7 @@ static int make_tmap_dw(CUtensorMap* map, const void* ptr, int n, int T, int H, 
     if (kt == 1) {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kTlCS, iw, 2, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kTlCS, iw, (cuuint32_t)(stride == 1 ? 2 : 1), 1};      // rows per stage: TailCfg::RPS
         r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
@@ -497,11 +515,9 @@ struct TailArgs {
     __half* out;
     int n, T, H, W, C, kt, stride, rd, N;
     int rows_per_chunk;      // 0: default
-    int lag;                 // 0: default
 };
 
 static int g_tail_rows = getenv("MDS_TAIL_ROWS") ? atoi(getenv("MDS_TAIL_ROWS")) : 12;
-static long long g_tail_l2_bytes = getenv("MDS_TAIL_L2_MB") ? atoll(getenv("MDS_TAIL_L2_MB")) << 20 : (24LL << 20);
 
 template <int KT, int STRIDE>
 static int launch_tail_t(const CUtensorMap& tmDw, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBias,
@@ -510,7 +526,7 @@ static int launch_tail_t(const CUtensorMap& tmDw, const CUtensorMap& tmA, const 
     auto kern = mbconv_tail_kernel<KT, STRIDE>;
     p.g_stages = 4;
     size_t smem = tl_smem_bytes(Cfg::DW_RING, p.N, p.g_stages, KT);
-    if (smem > 227 * 1024) { p.g_stages = 3; smem = tl_smem_bytes(Cfg::DW_RING, p.N, p.g_stages, KT); }
+    while (smem > 227 * 1024 && p.g_stages > 2) smem = tl_smem_bytes(Cfg::DW_RING, p.N, --p.g_stages, KT);
     if (smem > 227 * 1024) return fail(MDS_ERR_INVALID, "mbconv_tail: N=%d needs %zu bytes of shared memory", p.N, smem);
     {
         static size_t smem_set[kMaxDevices] = {};
@@ -522,7 +538,8 @@ static int launch_tail_t(const CUtensorMap& tmDw, const CUtensorMap& tmA, const 
         }
     }
     int grid = num_sms();
-    if (p.n_items < grid) grid = p.n_items;
+    const int n_dw = p.n * p.dw_per_img, n_tiles = p.n * p.tiles_per_img;
+    if (n_dw < grid && n_tiles < grid) grid = n_dw > n_tiles ? n_dw : n_tiles;
     ProfScope ps(KT == 1 ? MDS_KIND_TAIL2D : MDS_KIND_TAIL3D, st);
     launch_pdl(kern, dim3(grid), dim3(kTlThreads), smem, st, tmDw, tmA, tmB, tmBias, p);
     LAUNCH_CHECK("mbconv_tail");
@@ -561,17 +578,10 @@ static int launch_tail(const TailArgs& a, cudaStream_t st) {
     p.dw_per_img = a.T * p.chunks * p.xtiles * p.slab_pairs;
     p.rows_per_img = a.T * p.Ho * p.Wo;
     p.N = a.N;
-    p.tiles_per_img = a.N ? (p.rows_per_img + kTcBM - 1) / kTcBM : 0;
+    p.tiles_per_img = (a.N && !g_tail_dw_only) ? (p.rows_per_img + kTcBM - 1) / kTcBM : 0;
     p.num_kb = (a.C + kTcBK - 1) / kTcBK;
-    // images per block of the item order: as many as keep ~2.5 blocks of depthwise output inside L2
-    const long long img_bytes = (long long)p.rows_per_img * a.C * 2;
-    long long lag = a.lag > 0 ? a.lag : g_tail_l2_bytes / (img_bytes > 0 ? img_bytes : 1);
-    if (lag < 2) lag = 2;
-    if (lag > a.n || a.N == 0) lag = a.n;
-    p.lag = (int)lag;
-    const long long items = (long long)a.n * (p.dw_per_img + p.tiles_per_img);
-    if (items >= (1LL << 31)) return fail(MDS_ERR_INVALID, "mbconv_tail: too many work items");
-    p.n_items = (int)items;
+    if ((long long)a.n * p.dw_per_img >= (1LL << 31) || (long long)a.n * p.tiles_per_img >= (1LL << 31))
+        return fail(MDS_ERR_INVALID, "mbconv_tail: too many work items");
     int cols = 32;
     while (cols < 2 * (a.N ? a.N : 16)) cols <<= 1;
     p.tmem_cols = cols;
@@ -588,6 +598,77 @@ static int launch_tail(const TailArgs& a, cudaStream_t st) {
     if (a.kt == 3) return launch_tail_t<3, 1>(tmDw, tmA, tmB, tmBias, p, st);
     if (a.stride == 1) return launch_tail_t<1, 1>(tmDw, tmA, tmB, tmBias, p, st);
     return launch_tail_t<1, 2>(tmDw, tmA, tmB, tmBias, p, st);
+}
+
+
+// ---- TMA-staged depthwise + SE (dwconv_tma.cuh) ----
+static int g_dw_rows2d = getenv("MDS_DW_ROWS") ? atoi(getenv("MDS_DW_ROWS")) : 12;
+static int g_dw_rows3d = getenv("MDS_DW_ROWS3D") ? atoi(getenv("MDS_DW_ROWS3D")) : 8;
+template <int KT, int STRIDE>
+static int launch_dw_se_t(const CUtensorMap& tm, const DwSeParams& p, dim3 grid, cudaStream_t st) {
+    using Cfg = DwTmaCfg<KT, STRIDE>;
+    auto kern = dwconv_tma_kernel<KT, STRIDE>;
+    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
+    ProfScope ps(KT == 1 ? MDS_KIND_DWCONV2D : MDS_KIND_DWCONV3D, st);
+    launch_pdl(kern, grid, dim3(256), Cfg::SMEM, st, tm, p);
+    LAUNCH_CHECK("dwconv_tma");
+    return MDS_OK;
+}
+static int launch_dw_se(const __half* in, __half* out, const float* w, const float* bias, float* partials, int* nparts_out,
+                        const float* se_w1, const float* se_b1, const float* se_w2t, const float* se_b2, float* gate, int* done,
+                        int n, int T, int H, int W, int C, int kt, int stride, int rd, int rows_per_chunk, cudaStream_t st) {
+    if (C % 8 || C > 1152) return fail(MDS_ERR_INVALID, "dwconv_tma: C must be a multiple of 8, <= 1152");
+    if (!((kt == 1 && (stride == 1 || stride == 2)) || (kt == 3 && stride == 1)))
+        return fail(MDS_ERR_INVALID, "dwconv_tma: unsupported kt=%d stride=%d", kt, stride);
+    if (kt == 1 && T != 1) return fail(MDS_ERR_INVALID, "dwconv_tma 2D: T must be 1");
+    if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "dwconv_tma: stride-2 input must be even");
+    if (se_w1 && (rd <= 0 || rd > 64 || !gate || !done)) return fail(MDS_ERR_INVALID, "dwconv_tma: bad SE arguments");
+    if (n <= 0) return MDS_OK;
+    if (n > 65535) return fail(MDS_ERR_INVALID, "dwconv_tma: n too large");
+    DwSeParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.w = w; p.bias = bias; p.partials = partials; p.se_w1 = se_w1; p.se_b1 = se_b1; p.se_w2t = se_w2t; p.se_b2 = se_b2;
+    p.gate = gate; p.done = done; p.n = n; p.T = T; p.H = H; p.W = W; p.C = C; p.Ho = H / stride; p.Wo = W / stride; p.rd = rd;
+    p.inv_count = 1.0f / (float)((size_t)T * p.Ho * p.Wo);
+    // row chunks depend on the layer shape only: the squeeze sums of an image never depend on the rest of the batch
+    const int want = rows_per_chunk > 0 ? rows_per_chunk : (kt == 3 ? g_dw_rows3d : g_dw_rows2d);
+    int chunks = (p.Ho + want / 2) / want;
+    if (chunks < 1) chunks = 1;
+    p.xtiles = (p.Wo + kDtTWX - 1) / kDtTWX;
+    while (chunks > 1 && (long long)chunks * T * p.xtiles > kDwMaxParts) --chunks;
+    p.rows_per_chunk = (p.Ho + chunks - 1) / chunks;
+    p.chunks = (p.Ho + p.rows_per_chunk - 1) / p.rows_per_chunk;
+    p.slabs = (C + kDtCS - 1) / kDtCS;
+    p.nparts = p.chunks * T * p.xtiles;
+    if (p.nparts > kDwMaxParts) return fail(MDS_ERR_INVALID, "dwconv_tma: %d squeeze partials per image exceed %d", p.nparts, kDwMaxParts);
+    if (nparts_out) *nparts_out = p.nparts;
+    p.ctas_per_img = T * p.chunks * p.xtiles * p.slabs;
+    if ((long long)p.chunks * T > 65535) return fail(MDS_ERR_INVALID, "dwconv_tma: too many row chunks");
+
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    CUtensorMap tm;
+    const cuuint32_t iw = stride == 1 ? kDtTWX + 2 : 2 * kDtTWX + 1;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r;
+    if (kt == 1) {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kDtCS, iw, (cuuint32_t)(stride == 1 ? 3 : 2), 1};       // rows per stage: DwTmaCfg::RPS
+        r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)n};
+        cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)T * H * W * C * 2};
+        cuuint32_t box[5] = {(cuuint32_t)kDtCS, iw, 1, 3, 1};
+        r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled(dwconv_tma) failed (%d) n=%d T=%d H=%d W=%d C=%d", (int)r, n, T, H, W, C);
+    dim3 grid(p.xtiles * p.slabs, p.chunks * T, n);
+    if (kt == 3) return launch_dw_se_t<3, 1>(tm, p, grid, st);
+    if (stride == 1) return launch_dw_se_t<1, 1>(tm, p, grid, st);
+    return launch_dw_se_t<1, 2>(tm, p, grid, st);
 }
 
 static size_t gem_part_floats(int b, int T, int C) { return (size_t)b * T * kGemSplit * C; }
@@ -932,16 +1013,25 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
                 TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, b.w2, b.b2, cs, hh, ww, b.cin, b.mid, b.stride, b.cout, b.skip, st));
             } else {
                 TRY(launch_gemm(X[cur], b.wpw, b.bpw, nullptr, nullptr, M1, (long long)hh * ww, cs, b.mid, b.cin, 1, st, b.bmpw));
-                if (g_fused_tail) {
+                if (g_tail_mode == 1) {
                     TailArgs a;
                     a.m1 = M1; a.m2 = M2; a.dw_w = b.wdw; a.dw_b = b.bdw; a.se_w1 = b.se_w1; a.se_b1 = b.se_b1; a.se_w2t = b.se_w2t;
                     a.se_b2 = b.se_b2; a.partials = partials; a.gate = gate32; a.sync = h->sync; a.sync_stride = kSyncSlots;
                     a.wpwl = b.wpwl; a.bm = b.bmpwl; a.res = b.skip ? X[cur] : nullptr; a.out = X[cur ^ 1];
                     a.n = cs; a.T = 1; a.H = hh; a.W = ww; a.C = b.mid; a.kt = 1; a.stride = b.stride; a.rd = b.rd; a.N = b.cout;
-                    a.rows_per_chunk = 0; a.lag = 0;
+                    a.rows_per_chunk = 0;
                     TRY(launch_tail(a, st));
+                } else if (g_tail_mode == 2) {
+                    TRY(launch_dw_se(M1, M2, b.wdw, b.bdw, partials, nullptr, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate32, h->sync,
+                                     cs, 1, hh, ww, b.mid, 1, b.stride, b.rd, 0, st));
+                    TRY(launch_gemm_tc_stream(M2, b.wpwl, b.bmpwl, b.skip ? X[cur] : nullptr, X[cur ^ 1], ho * wo, cs, b.cout, b.mid, 0, st,
+                                              gate32));
                 } else {
                     int nparts = 0;
+                    if (g_tail_mode == 3)
+                        TRY(launch_dw_se(M1, M2, b.wdw, b.bdw, partials, &nparts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                         cs, 1, hh, ww, b.mid, 1, b.stride, b.rd, 0, st));
+                    else
                     TRY(launch_dw(M1, M2, b.wdw, b.bdw, partials, &nparts, cs, 1, hh, ww, b.mid, 1, b.stride, st));
                     TRY(launch_se(partials, nparts, b.se_w1, b.se_b1, b.se_w2t, b.se_b2, gate, b.w32pwl, wg, cs, b.mid, b.rd, b.cout,
                                   1.0f / (float)(ho * wo), st));
@@ -987,16 +1077,24 @@ static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int
     for (const Block3d& blk : h->blocks3d) {
         ++g_prof_tag;
         TRY(launch_gemm(x, blk.wpw, blk.bpw, nullptr, nullptr, M1, (long long)T * P, b, mid, c3, 1, st, blk.bmpw));
-        if (g_fused_tail && b <= kSyncSlots) {
+        if (g_tail_mode == 1 && b <= kSyncSlots) {
             TailArgs a;
             a.m1 = M1; a.m2 = M2; a.dw_w = blk.wdw; a.dw_b = blk.bdw; a.se_w1 = blk.se_w1; a.se_b1 = blk.se_b1; a.se_w2t = blk.se_w2t;
             a.se_b2 = blk.se_b2; a.partials = partials; a.gate = gate32; a.sync = h->sync; a.sync_stride = kSyncSlots;
             a.wpwl = blk.wpwl; a.bm = blk.bmpwl; a.res = x; a.out = Y[nxt];
             a.n = b; a.T = T; a.H = fh; a.W = fw; a.C = mid; a.kt = 3; a.stride = 1; a.rd = rd; a.N = c3;
-            a.rows_per_chunk = 0; a.lag = 0;
+            a.rows_per_chunk = 0;
             TRY(launch_tail(a, st));
+        } else if (g_tail_mode == 2 && b <= kSyncSlots) {
+            TRY(launch_dw_se(M1, M2, blk.wdw, blk.bdw, partials, nullptr, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate32, h->sync,
+                             b, T, fh, fw, mid, 3, 1, rd, 0, st));
+            TRY(launch_gemm_tc_stream(M2, blk.wpwl, blk.bmpwl, x, Y[nxt], T * P, b, c3, mid, 0, st, gate32));
         } else {
             int nparts = 0;
+            if (g_tail_mode == 3)
+                TRY(launch_dw_se(M1, M2, blk.wdw, blk.bdw, partials, &nparts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                 b, T, fh, fw, mid, 3, 1, rd, 0, st));
+            else
             TRY(launch_dw(M1, M2, blk.wdw, blk.bdw, partials, &nparts, b, T, fh, fw, mid, 3, 1, st));
             TRY(launch_se(partials, nparts, blk.se_w1, blk.se_b1, blk.se_w2t, blk.se_b2, gate, blk.w32pwl, wg, b, mid, rd, c3,
                           1.0f / (float)((size_t)T * P), st));
@@ -1155,10 +1253,24 @@ extern "C" int mds_k_gemm_gated(const void* A, const void* wg, const void* bias_
                                  reinterpret_cast<const __half*>(bias_mat), reinterpret_cast<const __half*>(res),
                                  reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream));
 }
+extern "C" int mds_k_dwconv_se(const void* in, void* out, const float* w, const float* bias, float* partials, int* nparts,
+                               const float* se_w1, const float* se_b1, const float* se_w2t, const float* se_b2, float* gate, int* done,
+                               int n, int T, int H, int W, int C, int kt, int stride, int rd, int rows_per_chunk, void* stream) {
+    if (!in || !out || !w || !bias || !partials) return fail(MDS_ERR_INVALID, "dwconv_se: null argument");
+    return launch_dw_se(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), w, bias, partials, nparts, se_w1, se_b1,
+                        se_w2t, se_b2, gate, done, n, T, H, W, C, kt, stride, rd, rows_per_chunk, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mds_k_gemm_gate(const void* A, const void* W, const float* gate, const void* bias_mat, const void* res, void* C,
+                               int rows_per_img, int n_img, int N, int K, int act, void* stream) {
+    if (!gate) return fail(MDS_ERR_INVALID, "gemm_gate: null gate");
+    return launch_gemm_tc_stream(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(W),
+                                 reinterpret_cast<const __half*>(bias_mat), reinterpret_cast<const __half*>(res),
+                                 reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream), gate);
+}
 extern "C" int mds_k_mbconv_tail(const void* m1, void* m2, const float* dw_w, const float* dw_b, float* partials, const float* se_w1,
                                  const float* se_b1, const float* se_w2t, const float* se_b2, float* gate, int* sync, const void* wpwl,
                                  const void* bias_mat, const void* res, void* out, int n, int T, int H, int W, int C, int kt, int stride,
-                                 int rd, int N, int rows_per_chunk, int lag, void* stream) {
+                                 int rd, int N, int rows_per_chunk, void* stream) {
     if (!m1 || !m2 || !dw_w || !dw_b || !partials || !se_w1 || !se_b1 || !se_w2t || !se_b2 || !gate || !sync)
         return fail(MDS_ERR_INVALID, "mbconv_tail: null argument");
     if (N && (!wpwl || !bias_mat || !out)) return fail(MDS_ERR_INVALID, "mbconv_tail: null projection argument");
@@ -1168,7 +1280,7 @@ extern "C" int mds_k_mbconv_tail(const void* m1, void* m2, const float* dw_w, co
     a.sync = sync; a.sync_stride = n; a.wpwl = reinterpret_cast<const __half*>(wpwl); a.bm = reinterpret_cast<const __half*>(bias_mat);
     a.res = reinterpret_cast<const __half*>(res); a.out = reinterpret_cast<__half*>(out);
     a.n = n; a.T = T; a.H = H; a.W = W; a.C = C; a.kt = kt; a.stride = stride; a.rd = rd; a.N = N;
-    a.rows_per_chunk = rows_per_chunk; a.lag = lag;
+    a.rows_per_chunk = rows_per_chunk;
     return launch_tail(a, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int mds_k_gem(const void* x, float* feat, int b, int T, int P, int C, float p, float eps, void* stream) {

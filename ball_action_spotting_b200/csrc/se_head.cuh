@@ -118,14 +118,19 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
         return reinterpret_cast<const float4*>(p.w32 + (size_t)o * p.C + c_lo + gq * 8);
     };
     int i = tid;
-    for (; i + kSeThreads < total; i += 2 * kSeThreads) {      // two items (four 16-byte loads) in flight per thread
-        const float4* s0 = src(i);
+    for (; i + 3 * kSeThreads < total; i += 4 * kSeThreads) {  // four items (eight 16-byte loads) in flight per thread: this loop is a
+        const float4* s0 = src(i);                             // chain of L2 round trips, so its time is the number of trips
         const float4* s1 = src(i + kSeThreads);
+        const float4* s2 = src(i + 2 * kSeThreads);
+        const float4* s3 = src(i + 3 * kSeThreads);
         const float4 a0 = __ldg(s0), a1 = __ldg(s0 + 1), b0 = __ldg(s1), b1 = __ldg(s1 + 1);
+        const float4 c0 = __ldg(s2), c1 = __ldg(s2 + 1), d0 = __ldg(s3), d1 = __ldg(s3 + 1);
         gate8(i, a0, a1);
         gate8(i + kSeThreads, b0, b1);
+        gate8(i + 2 * kSeThreads, c0, c1);
+        gate8(i + 3 * kSeThreads, d0, d1);
     }
-    if (i < total) {
+    for (; i < total; i += kSeThreads) {
         const float4* s0 = src(i);
         const float4 a0 = __ldg(s0), a1 = __ldg(s0 + 1);
         gate8(i, a0, a1);

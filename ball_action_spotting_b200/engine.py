@@ -54,9 +54,11 @@ class Engine:
         check(self.lib.mds_create(C.byref(c), C.byref(h)), "mds_create")
         self._h = h
         self._ws: Optional[torch.Tensor] = None
+        self.version = 0          # bumped by every load_packed(): captured CUDA graphs of older versions must be rebuilt
         self.load_packed(packed)
 
     def load_packed(self, packed: Dict[str, torch.Tensor]) -> None:
+        self.version += 1
         for name, t in packed.items():
             t = t.contiguous().cpu()
             check(self.lib.mds_weights_add(self._h, name.encode(), t.data_ptr(), t.numel() * t.element_size()),

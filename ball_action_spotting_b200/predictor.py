@@ -41,15 +41,29 @@ class LoadedModel:
         return self.nn_module
 
 
-def load_model(model_path, device: str = "cuda:0") -> LoadedModel:
-    """Reads the ``EmaCheckpoint`` dict (src/ema.py:71-76): {model_name, params, nn_state_dict, ...}."""
-    state = torch.load(str(model_path), map_location="cpu", weights_only=False)
+def _load_checkpoint(model_path) -> dict:
+    """torch.load restricted to tensors and plain containers (the EmaCheckpoint dict holds nothing else); a checkpoint
+    that needs arbitrary unpickling is only loaded when MDS_UNSAFE_LOAD=1."""
+    import os
+    import pickle
+    try:
+        return torch.load(str(model_path), map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError:
+        if os.environ.get("MDS_UNSAFE_LOAD") == "1":
+            return torch.load(str(model_path), map_location="cpu", weights_only=False)
+        raise
+
+
+def load_model(model_path, device: str = "cuda:0", bias_correction: bool = True) -> LoadedModel:
+    """Reads the ``EmaCheckpoint`` dict (src/ema.py:71-76): {model_name, params, nn_state_dict, ...}.
+    bias_correction: packer.py's data-free correction of the fp16 weight-rounding bias (off = the exact folded parameters)."""
+    state = _load_checkpoint(model_path)
     params = state["params"]
     name, kwargs = params["nn_module"]
     assert name == "multidim_stacker"                                     # predictors.py:26
     kwargs = dict(kwargs)
     kwargs["pretrained"] = False
-    module = MultiDimStacker(**kwargs)
+    module = MultiDimStacker(**kwargs, bias_correction=bias_correction)
     module.load_state_dict(state["nn_state_dict"])
     dev = torch.device(device[0] if isinstance(device, (list, tuple)) else device)
     module.to(dev).eval()
@@ -84,6 +98,7 @@ class _FrameGraphs:
         with torch.cuda.graph(self.g3d):
             self.pred = predictor._head(eng, self.stack)                 # (num_classes,) float32
         self._ws = eng._ws          # the recorded launches point into this workspace: keep it alive if the engine grows a new one
+        self.version = eng.version  # weights (and gem_p, a kernel argument) are baked into the recording
 
     def encode(self, frames) -> torch.Tensor:
         for i, f in enumerate(frames):
@@ -99,8 +114,9 @@ class _FrameGraphs:
 
 
 class MultiDimStackerPredictor:
-    def __init__(self, model_path: Path, device: str = "cuda:0", tta: bool = False, cuda_graph: bool = True):
-        self.model = load_model(model_path, device=device)
+    def __init__(self, model_path: Path, device: str = "cuda:0", tta: bool = False, cuda_graph: bool = True,
+                 bias_correction: bool = True):
+        self.model = load_model(model_path, device=device, bias_correction=bias_correction)
         self.cuda_graph = cuda_graph
         self._graphs: Optional[_FrameGraphs] = None
         self.model.eval()
@@ -159,7 +175,8 @@ class MultiDimStackerPredictor:
         self._clear_old(predict_indexes[0])
         if set(predict_indexes) <= set(self._frame_index2frame.keys()):
             eng = self.model.nn_module.engine(self.device)
-            if self.cuda_graph and (self._graphs is None or self._graphs.frames.shape[-2:] != frame.shape[-2:]):
+            if self.cuda_graph and (self._graphs is None or self._graphs.frames.shape[-2:] != frame.shape[-2:]
+                                    or self._graphs.version != eng.version):        # re-packed weights invalidate the recording
                 self._graphs = _FrameGraphs(self, frame.shape[-2], frame.shape[-1])
             stacks_indexes = list(batched(predict_indexes, self.model_stack_size))
             for stack_indexes in stacks_indexes:

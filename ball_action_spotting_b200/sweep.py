@@ -2,7 +2,8 @@
 ``src/predictors.py``) and its multi-GPU sharding.
 
 The streaming predictor computes, for every new frame, ONE encoder pass (the new triple) and one 3D/head pass.  The
-sweep does exactly the same work for a whole buffer of frames at once:
+sweep does the same work for a whole buffer of frames at once (plus hop*(T-1) = 24 re-encoded triples per buffer of
+`buffer_frames` frames, 1.2 % at the default 2048):
   * every triple start s in the buffer is one encoder image (frames s, s+step, s+2*step): the stem kernel addresses
     them in place with img_stride = 1 frame and plane_stride = `step` frames — no gather, no copy;
   * prediction p stacks the cached features of the triples starting at p-behind + 3*step*j, j = 0..T-1;
@@ -84,17 +85,18 @@ class SlidingSweep:
         eng = self.module.engine(frames.device)
         W, H = self.image_size
         hop = self.step * self.stack_size                      # frames between consecutive triples of one window
+        # every triple start needed by [a, b) is encoded exactly once (the engine walks them in chunk_images passes);
+        # the 3D blocks + head then run over windows of the cached features, max_stacks predictions at a time
+        s_lo = a - self.gen.behind                             # first triple start
+        s_hi = (b - 1) - self.gen.behind + hop * (self.T - 1)
+        n_img = s_hi - s_lo + 1
+        feats = []
+        for flip in ((False, True) if self.tta else (False,)):
+            desc = eng.frames_desc(frames, H, W, h * w, self.step * h * w, hflip=flip, offset_elems=(s_lo - first_frame) * h * w)
+            feats.append(eng.forward_2d(desc, n_img))          # (n_img, fh, fw, 192)
         out = []
         for c0 in range(a, b, self.max_stacks):
             c1 = min(b, c0 + self.max_stacks)
-            s_lo = c0 - self.gen.behind                        # first triple start needed by this chunk
-            s_hi = (c1 - 1) - self.gen.behind + hop * (self.T - 1)
-            n_img = s_hi - s_lo + 1
-            feats = []
-            for flip in ((False, True) if self.tta else (False,)):
-                desc = eng.frames_desc(frames, H, W, h * w, self.step * h * w, hflip=flip,
-                                       offset_elems=(s_lo - first_frame) * h * w)
-                feats.append(eng.forward_2d(desc, n_img))      # (n_img, fh, fw, 192)
             probs = None
             for f in feats:     # window p = cached features of the triples starting at p - behind + hop * t (predictors.py:58-68)
                 x = eng.gather_stacks(f, c0 - self.gen.behind - s_lo, hop, c1 - c0, self.T)    # (n_pred, T, fh, fw, 192)
@@ -107,7 +109,7 @@ class SlidingSweep:
 
 
 def sweep_video(sweep: SlidingSweep, frame_source: Callable[[int, int], torch.Tensor], frame_count: int, save_zone: int = 1,
-                rank: int = 0, world: int = 1, group=None, buffer_frames: int = 512):
+                rank: int = 0, world: int = 1, group=None, buffer_frames: int = 2048):
     """Predict a whole video, sharded over `world` ranks.  frame_source(i0, i1) returns uint8 frames [i0, i1) on this
     rank's GPU (decode / synthetic).  Returns (frame_indexes, predictions (N, C)) on every rank."""
     lo, hi = prediction_bounds(sweep.gen, frame_count, save_zone)

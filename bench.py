@@ -30,14 +30,24 @@ H, W, STORED_H, FRAMES = 736, 1280, 720, 15
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=4, help="frame-stacks per GPU per step (configs[1] = 4, configs[2] = 32)")
     ap.add_argument("--chunk-images", type=int, default=0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="full", choices=["full", "sweep"],
+                    help="full: FULL forward (configs[1]/[2], the headline); sweep: SLIDING synthetic-match sweep (configs[3])")
+    ap.add_argument("--sweep-frames", type=int, default=67500, help="frames per half (45 min x 25 fps)")
+    ap.add_argument("--tta", type=int, default=0)
+    ap.add_argument("--tail-mode", type=int, default=3, choices=[0, 1, 2, 3],
+                    help="MBConv tails: 3 = TMA depthwise + SE kernel + GEMM (default), 2 = depthwise+SE kernel and gating GEMM, 1 = one fused launch, 0 = round-1 path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.steps_given = a.steps is not None
+    if a.steps is None:
+        a.steps = 20
+    return a
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -180,6 +190,7 @@ def run_b200(args):
     net.init_random_(seed=1234)
     net.to(dev).eval()
     eng = net.engine(dev)
+    eng.lib.mds_set_tail_mode(args.tail_mode)
 
     # synthetic uint8 frames; R rotating batches so that consecutive steps never re-read the same input from L2
     bytes_in = B * FRAMES * STORED_H * W
@@ -289,7 +300,7 @@ def run_b200(args):
         per_kind_ms = {}
         for kind, tag, t in recs:
             per_kind_ms[kind] = per_kind_ms.get(kind, 0.0) + t
-        tot = acc.per_stack_totals(H, W, STORED_H, T)
+        tot = acc.per_stack_totals(H, W, STORED_H, T, tail_mode=0 if args.tail_mode == 3 else args.tail_mode)
         peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
@@ -322,6 +333,49 @@ def run_b200(args):
                     "unit": top[1]["unit"], "frac": top[1]["frac"], "traffic": top[1]["traffic"],
                     "peak_source": peaks["src"], "timing": f"per-launch CUDA events on the launching stream, {PK} steps"}
 
+    # ---- depthwise stage alone (SURVEY.md 8(d) "DW-only" bytes, the north_star's >= 60 % figure) ----
+    roofline_dw = None
+    if rank == 0 and by_kind:
+        dwb = acc.depthwise_only_bytes(H, W, T)
+        if any(k in by_kind for k in ("tail2d", "tail3d")):
+            # fused build: the depthwise items of the fused tail kernels are timed by running the same launches with their
+            # projection items switched off (mds_set_tail_dw_only); outputs of these passes are discarded
+            eng.lib.mds_set_tail_dw_only(1)
+            for i in range(2):
+                step_local(i)
+            torch.cuda.synchronize()
+            eng.profile_begin()
+            for i in range(PK):
+                step_local(i)
+            recs_dw = eng.profile_end()
+            eng.lib.mds_set_tail_dw_only(0)
+            step_local(0)
+            torch.cuda.synchronize()
+            ms2 = sum(t for k, _, t in recs_dw if k == 11) / PK
+            ms3 = sum(t for k, _, t in recs_dw if k == 12) / PK
+            how = "depthwise + SE items of the fused tail kernels, projection items off (mds_set_tail_dw_only)"
+        else:
+            ms2, ms3 = by_kind["dwconv2d"]["ms_per_step"], by_kind["dwconv3d"]["ms_per_step"]
+            how = "dwconv_tma kernels (depthwise + squeeze + SE MLP of the last CTA)" if args.tail_mode == 2 else "round-1 dwconv kernels"
+        g2 = dwb["dwconv2d"] * B / (ms2 / 1e3) / 1e9 if ms2 > 0 else 0.0
+        g3 = dwb["dwconv3d"] * B / (ms3 / 1e3) / 1e9 if ms3 > 0 else 0.0
+        roofline_dw = {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["src"],
+                       "achieved": g2, "frac": g2 / peaks["hbm_gbs"], "ms_per_step": ms2,
+                       "bytes_per_stack": dwb["dwconv2d"], "what": "16 depthwise 3x3 layers x 5 images: read mid x H x W + write mid x Ho x Wo, fp16",
+                       "dw3d": {"achieved": g3, "frac": g3 / peaks["hbm_gbs"], "ms_per_step": ms3, "bytes_per_stack": dwb["dwconv3d"]},
+                       "timing": how + f", per-launch CUDA events, {PK} steps"}
+
+    # ---- platform ceiling of the e2e leg: the same pinned host -> device copies alone, all ranks at once ----
+    def h2d_only(i):
+        s_ = i & 1
+        with torch.cuda.stream(copy_stream):
+            stage[s_].copy_(host[i % len(host)], non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+    for i in range(2):
+        h2d_only(i)
+    ms_h2d = timed(h2d_only, K)
+    h2d_gbs = world * bytes_in * K / (ms_h2d / 1e3) / 1e9
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times, cores = cpu_forward_timer(args.cpu_steps, 1)
@@ -339,11 +393,138 @@ def run_b200(args):
                            "chunk_images": eng.cfg.chunk_images or 160},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": B * 2 * 4,
-                        "ms_per_step": ms_e2e / K},
+                        "ms_per_step": ms_e2e / K, "h2d_ceiling_gbs": h2d_gbs,
+                        "h2d_ceiling_stacks_per_s": world * B * K / (ms_h2d / 1e3),
+                        "h2d_ceiling_note": "the same pinned-host -> device copies with no compute, all ranks at once"},
                 "gpu_launches": launches,
-                "roofline": roofline, "roofline_by_kind": by_kind, "cpu_baseline": cpu_baseline}
+                "bias_correction": bool(net._bias_correction),
+                "roofline": roofline, "roofline_dw": roofline_dw, "roofline_by_kind": by_kind, "cpu_baseline": cpu_baseline,
+                "mbconv_tail": {2: "dwconv_tma (depthwise + SE) + gating GEMM: 2 launches", 1: "mbconv_tail: 1 launch",
+                                0: "round-1 path: dwconv + se_fc + gated GEMM: 3 launches",
+                                3: "dwconv_tma + se_fc + pre-gated GEMM: 3 launches"}[args.tail_mode]}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: full synthetic-match sweep (SLIDING semantics), sharded over the GPUs, one all-gather per half
+# ------------------------------------------------------------------------------------------------------------------
+def synthetic_video(dev, h=STORED_H, w=W, seed=1234, block=64):
+    """Deterministic synthetic video: frame i is generated on the device from (seed, i // block), so a 45-minute half
+    (62 GB of uint8 frames) never exists as a whole and every rank can produce exactly the frames of its shard."""
+    import torch
+    cache = {}
+
+    def block_frames(bi):
+        if bi not in cache:
+            if len(cache) > 40:
+                cache.pop(next(iter(cache)))
+            g = torch.Generator(device=dev).manual_seed(seed * 100003 + bi)
+            cache[bi] = torch.randint(0, 256, (block, h, w), dtype=torch.uint8, device=dev, generator=g)
+        return cache[bi]
+
+    def source(i0, i1):
+        parts = []
+        for bi in range(i0 // block, (i1 - 1) // block + 1):
+            lo, hi = max(i0, bi * block), min(i1, (bi + 1) * block)
+            parts.append(block_frames(bi)[lo - bi * block: hi - bi * block])
+        return torch.cat(parts, 0).contiguous()
+    return source
+
+
+def run_sweep(args):
+    """One step = one half of a match (args.sweep_frames frames, scripts/ball_action/predict.py:29-55 semantics: every
+    frame index in [clip(0), clip(frame_count)] gets one prediction from its 15-frame window).  The prediction range of a
+    half is split into `world` contiguous shards (28-frame halo), one all-gather of the (n, 2) probabilities per half."""
+    import torch
+    import torch.distributed as dist
+    from ball_action_spotting_b200 import MultiDimStacker
+    from ball_action_spotting_b200 import postprocess as PP
+    from ball_action_spotting_b200.sweep import SlidingSweep, prediction_bounds, shard_range, sweep_video
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device — the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    halves = max(1, min(args.steps, 2)) if args.steps_given else 2
+    Wm = max(3, args.warmup)
+    net = MultiDimStacker("tf_efficientnetv2_b0.in1k", 2, num_frames=FRAMES, stack_size=3, num_3d_blocks=4,
+                          expansion_3d_ratio=3, se_reduce_3d_ratio=24).init_random_(seed=1234).to(dev).eval()
+    eng = net.engine(dev)
+    sweep = SlidingSweep(net, FRAMES, 2, (W, H), tta=bool(args.tta), max_stacks=128)
+    sources = [synthetic_video(dev, seed=1234 + hf) for hf in range(halves)]
+    F = args.sweep_frames
+    lo, hi = prediction_bounds(sweep.gen, F, 1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):                                   # warm-up: short excerpts (also builds the NCCL communicator)
+        sweep_video(sweep, sources[0], min(F, 400), 1, rank, world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.launch_count(reset=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    results = [sweep_video(sweep, sources[hf], F, 1, rank, world) for hf in range(halves)]
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    launches = eng.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    n_pred = (hi - lo + 1) * halves
+    if rank == 0:
+        frame_indexes, preds = results[0]
+        # ---- sharded == unsharded, checked where it can differ: windows that straddle every shard boundary ----
+        # (at world == 1 the same check runs against the boundaries an 8-way split would have: different batch composition)
+        vw = world if world > 1 else 8
+        checks, max_diff = [], 0.0
+        for r in range(1, vw):
+            bnd = shard_range(lo, hi, r, vw)[0]
+            a, b = max(lo, bnd - 24), min(hi + 1, bnd + 24)
+            f0, f1 = a - sweep.gen.behind, b - 1 + sweep.gen.ahead
+            single = sweep.predict_range(sources[0](f0, f1 + 1), f0, a, b)
+            d = float((single - preds[a - lo: b - lo]).abs().max())
+            max_diff = max(max_diff, d)
+            checks.append([a, b, d])
+        actions = PP.raw_predictions_to_actions(frame_indexes, preds, {"PASS": 0, "DRIVE": 1},
+                                                {"gauss_sigma": 3.0, "height": 0.2, "distance": 15}, device=str(dev))
+        host_preds = preds.cpu()
+        value = n_pred / (ms / 1e3)
+        line = {"metric": "SLIDING predictions/sec (15x1280x736 window, step 2)", "value": value, "unit": "predictions/s",
+                "n_gpus": world, "steps": halves, "warmup": Wm, "ms_per_step": ms / halves, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+                "config": {"workload": f"BASELINE.json configs[3]: synthetic match, {halves} halves x {F} uint8 720x1280 frames generated on the "
+                                       f"device per block, SLIDING semantics, tta={bool(args.tta)}", "frames_per_half": F,
+                           "predictions_per_half": hi - lo + 1, "sharding": f"prediction range x{world}, 28-frame halo, one all-gather of (n, 2) per half",
+                           "l2": "every frame is read once; 2048-frame buffers (1.9 GB) exceed L2"},
+                "video_fps_equivalent": F * halves / (ms / 1e3), "clocks": clocks,
+                "e2e": None, "e2e_note": "configs[3] synthesises frames on the device, so this mode has no host->device leg; "
+                                          f"the gathered predictions ({host_preds.numel() * 4} bytes per half) are copied to the host after the timed region",
+                "gpu_launches": launches,
+                "sharded_equals_unsharded": {"boundaries_checked": len(checks), "window": 48, "max_abs_diff": max_diff,
+                                             "bit_identical": max_diff == 0.0,
+                                             "how": "rank 0 recomputes, unsharded, the 48 predictions around every shard boundary "
+                                                    + ("of this run" if world > 1 else "an 8-way split would have")},
+                "spots": {k: len(v[0]) for k, v in actions.items()}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -351,6 +532,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "sweep":
+        run_sweep(args)
     else:
         run_b200(args)
 

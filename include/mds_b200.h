@@ -126,16 +126,29 @@ int mds_k_se_fc(const float* partials, int nparts, const float* w1, const float*
 /* SE-gated projection GEMM on tcgen05: C[img] = act(A[img] . wg[img]^T + bias) (+ res); N <= 256. */
 int mds_k_gemm_gated(const void* A, const void* wg, const void* bias_mat, const void* res, void* C, int rows_per_img,
                      int n_img, int N, int K, int act, void* stream);
+/* Depthwise conv + BN + SiLU with TMA-staged input rows, the SE squeeze and the SE excitation MLP in one launch (timm
+ * InvertedResidual conv_dw/bn2/se.conv_reduce/se.conv_expand; multidim_stacker.py:110-114, 72-90): out fp16 [n][T][H/s][W/s][C],
+ * gate f32 [n][C] = sigmoid(W2 SiLU(W1 mean + b1) + b2), evaluated by the CTA that finishes an image last.  partials: f32 scratch
+ * [n][64][C] (*nparts receives the number used); done: int scratch [n], ZERO on entry, left zero.  se_w1 = NULL: no SE (partials
+ * only).  rows_per_chunk: output rows per CTA, 0 = default (a function of the layer shape only). */
+int mds_k_dwconv_se(const void* in, void* out, const float* w, const float* bias, float* partials, int* nparts,
+                    const float* se_w1, const float* se_b1, const float* se_w2t, const float* se_b2, float* gate, int* done,
+                    int n, int T, int H, int W, int C, int kt, int stride, int rd, int rows_per_chunk, void* stream);
+/* SE-gated projection GEMM on tcgen05: C[img] = act((A[img] * gate[img]) . W^T + bias) (+ res) with the gate applied to the A
+ * blocks in shared memory (x * gate then conv_pwl + bn3 (+ shortcut), multidim_stacker.py:90,129-134); W fp16 [N][K], N <= 256,
+ * K <= 1152, gate f32 [n_img][K]. */
+int mds_k_gemm_gate(const void* A, const void* W, const float* gate, const void* bias_mat, const void* res, void* C,
+                    int rows_per_img, int n_img, int N, int K, int act, void* stream);
 /* Fused MBConv tail, ONE launch (timm InvertedResidual conv_dw/bn2/se/conv_pwl/bn3 (+ shortcut), built at
  * multidim_stacker.py:166-176; InvertedResidual3d multidim_stacker.py:110-134): m1 fp16 [n][T][H][W][C] (expanded input) ->
  * m2 fp16 [n][T][H/s][W/s][C] (depthwise + BN + SiLU, before gating), gate f32 [n][C] (SE excitation, SqueezeExcite :72-90),
  * out fp16 [n][T*(H/s)*(W/s)][N] = (m2 * gate) . wpwl^T + bias (+ res).  kt = 1 (2D, stride 1 or 2, T = 1) or 3 (3x3x3).
- * partials: f32 scratch [n][64][C]; sync: int scratch [3][n], must be ZERO on entry and is left zero (N > 0).
- * N = 0: depthwise + SE only (wpwl / bias_mat / res / out unused; sync is left non-zero).  rows_per_chunk / lag: 0 = default. */
+ * partials: f32 scratch [n][64][C]; sync: int scratch [3][n], must be ZERO on entry and is left zero.
+ * N = 0: depthwise + SE only (wpwl / bias_mat / res / out unused).  rows_per_chunk: output rows per depthwise item, 0 = default. */
 int mds_k_mbconv_tail(const void* m1, void* m2, const float* dw_w, const float* dw_b, float* partials, const float* se_w1,
                       const float* se_b1, const float* se_w2t, const float* se_b2, float* gate, int* sync, const void* wpwl,
                       const void* bias_mat, const void* res, void* out, int n, int T, int H, int W, int C, int kt, int stride,
-                      int rd, int N, int rows_per_chunk, int lag, void* stream);
+                      int rd, int N, int rows_per_chunk, void* stream);
 int mds_k_gem(const void* x, float* feat, int b, int T, int P, int C, float p, float eps, void* stream);
 int mds_k_linear(const float* feat, const float* w, const float* bias, float* out, int b, int F, int num_classes,
                  int apply_sigmoid, void* stream);
@@ -221,8 +234,14 @@ int mds_post_processing(const float* raw, int n_frames, int num_classes, const d
 /* Programmatic dependent launch of the forward chain (default on): each kernel's launch latency, CTA scheduling and
  * constant set-up overlap the previous kernel's tail.  0 restores plain stream serialization (A/B measurements). */
 int mds_set_pdl(int enabled);
-/* MBConv tails as one fused launch (default 1, mds_k_mbconv_tail) or as depthwise / SE / gated-GEMM launches (0; A/B runs). */
-int mds_set_fused_tail(int enabled);
+/* How the MBConv tails (depthwise + SE + projection) are launched (A/B measurements; all four are parity-tested).
+ * 3 (default): mds_k_dwconv_se without SE weights (TMA-staged depthwise + squeeze) + mds_k_se_fc + mds_k_gemm_gated;
+ * 2: mds_k_dwconv_se (incl. the SE MLP) + mds_k_gemm_gate; 1: mds_k_mbconv_tail (ONE persistent launch);
+ * 0: round-1 path mds_k_dwconv + mds_k_se_fc + mds_k_gemm_gated. */
+int mds_set_tail_mode(int mode);
+/* Measurement only (bench.py `roofline_dw`): 1 = the fused tails execute their depthwise + SE items alone, so that the
+ * depthwise stage can be timed by itself; forward outputs are NOT valid while this is set. */
+int mds_set_tail_dw_only(int enabled);
 
 /* number of kernels launched by this library in the calling thread since the last reset (bench "gpu_launches") */
 long long mds_launch_count(int reset);

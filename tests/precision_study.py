@@ -82,7 +82,26 @@ def make_variant(sd0, cfg, spec):
         r = torch.randint(0, 1 << 13, bits.shape, generator=gen, dtype=torch.int32)
         return ((bits + r) & ~((1 << 13) - 1)).view(torch.float32)
 
+    ed_re = [re.compile(s[3:]) for s in spec if s.startswith("ed:")]       # error diffusion along W (full row chain)
+    ep_re = [re.compile(s[3:]) for s in spec if s.startswith("ep:")]       # error feedback inside pixel pairs (w, w+1)
+
+    def diffuse(x, pair):
+        out = torch.empty_like(x)
+        carry = torch.zeros_like(x[..., 0])
+        for w_ in range(x.shape[-1]):
+            v = x[..., w_] + carry
+            q = v.half().float()
+            out[..., w_] = q
+            carry = v - q
+            if pair and (w_ & 1):
+                carry = torch.zeros_like(carry)
+        return out
+
     def tap(name, x):
+        if any(r.fullmatch(name) for r in ed_re):
+            return diffuse(x, False)
+        if any(r.fullmatch(name) for r in ep_re):
+            return diffuse(x, True)
         if any(r.fullmatch(name) for r in sr_re):
             return sround(x)
         if any(r.fullmatch(name) for r in act2_re):
@@ -114,6 +133,9 @@ VARIANTS = {
     "w_b20": [r"w:blocks\.2\.0\."], "w_b21": [r"w:blocks\.2\.1\."],
     "w_early_exp": [r"w:blocks\.[012]\.\d\.(conv|conv_exp)\."], "w_early_pwl": [r"w:blocks\.[012]\.\d\.conv_pwl"],
     "sr_all": ["sr:.*"], "sr_stem": ["sr:stem"], "sr_stream": [r"sr:(stem|b\d\.\d|proj2d|c3d\.\d)"],
+    "ed_stem": ["ed:stem"], "ep_stem": ["ep:stem"],
+    "ed_early": [r"ed:(stem|b[012]\.\d)"], "ep_early": [r"ep:(stem|b[012]\.\d)"], "rn_early": [r"act:(stem|b[012]\.\d)"],
+    "ed_stream": [r"ed:(stem|b\d\.\d)"], "rn_stream": [r"act:(stem|b\d\.\d)"],
     "optX": ["act:.*", r"wc:blocks\.[012]\."],
     "optY": ["act:.*"],
     # candidate builds: what stays fp16

@@ -17,11 +17,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--chunk-images", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--tail-mode", type=int, default=3)
 a = ap.parse_args()
 H, W, SH, T = 736, 1280, 720, 5
 dev = torch.device("cuda:0")
 net = MultiDimStacker("tf_efficientnetv2_b0.in1k", 2, num_3d_blocks=4, expansion_3d_ratio=3, chunk_images=a.chunk_images).init_random_(1).to(dev).eval()
 eng = net.engine(dev)
+eng.lib.mds_set_tail_mode(a.tail_mode)
 x = torch.randint(0, 256, (a.batch, 15, SH, W), dtype=torch.uint8, device=dev)
 desc = eng.frames_desc(x, H, W, 3 * SH * W, SH * W)
 for _ in range(2):
@@ -41,8 +43,8 @@ for i, (kind, tag, ms) in enumerate(recs):
     per[j] += ms
 launch = [(recs[j][0], recs[j][1]) for j in range(n_per_rep)]
 # expected launch list for one chunk of the encoder + 3D
-enc = acc.encoder_launches(H, W, SH)
-s3d = acc.stack3d_launches(H // 32, W // 32, T)
+enc = acc.encoder_launches(H, W, SH, tail_mode=0 if a.tail_mode == 3 else a.tail_mode)
+s3d = acc.stack3d_launches(H // 32, W // 32, T, tail_mode=0 if a.tail_mode == 3 else a.tail_mode)
 chunk = eng.cfg.chunk_images or 160
 n_img = a.batch * T
 chunks = -(-n_img // chunk)
