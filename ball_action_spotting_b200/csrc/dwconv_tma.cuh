@@ -50,8 +50,9 @@ struct DwTmaCfg {
     static constexpr int ROWB = IW * kDtCS * 2;                                // bytes of one input row tile (one plane)
     static constexpr int STAGEB = KT * RPS * ROWB;
     static constexpr int NST = 3;
-    // ring | s_part[8][64] | s_mean[1152] | s_hid[64] | s_w[27][64] (3D) | barriers
-    static constexpr size_t SMEM = 128 + (size_t)NST * STAGEB + (8 * 64 + 1152 + 64 + (KT == 3 ? 27 * 64 : 0)) * sizeof(float) + 64;
+    // ring (re-used after the row loop as s_part[8][64] | s_mean[1152] | s_hid[64]) | s_w[27][64] (3D) | barriers
+    static constexpr size_t SMEM = 128 + (size_t)NST * STAGEB + (KT == 3 ? 27 * 64 : 0) * sizeof(float) + 64;
+    static_assert((size_t)NST * STAGEB >= (8 * 64 + 1152 + 64) * sizeof(float), "the SE scratch aliases the ring");
 };
 
 __device__ __forceinline__ void dt_tma_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -89,10 +90,10 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
     extern __shared__ unsigned char dt_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dt_smem_raw) + 127) & ~uintptr_t(127));
     unsigned char* s_ring = smem;
-    float* s_part = reinterpret_cast<float*>(s_ring + (size_t)Cfg::NST * Cfg::STAGEB);     // [8][64]
-    float* s_mean = s_part + 8 * 64;                                                        // [1152]
-    float* s_hid = s_mean + 1152;                                                           // [64]
-    float* s_w = s_hid + 64;                                                                // [27][64] (KT == 3)
+    float* s_part = reinterpret_cast<float*>(s_ring);      // [8][64]   } alias the ring: only touched after the row loop, when every
+    float* s_mean = s_part + 8 * 64;                       // [1152]    } TMA load has landed and every warp has consumed its rows
+    float* s_hid = s_mean + 1152;                          // [64]      }
+    float* s_w = reinterpret_cast<float*>(s_ring + (size_t)Cfg::NST * Cfg::STAGEB);         // [27][64] (KT == 3)
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + (KT == 3 ? 27 * kDtCS : 0));
     uint64_t* full = bars;                // [3]
     uint64_t* empty = bars + 3;           // [3]
@@ -118,19 +119,30 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmIn) : "memory");
     }
-    // per-thread weights: 2D: 9 taps in registers; 3D: 27 taps do not fit next to the accumulators, they are staged in shared
-    // memory once per CTA and read per plane (LDS.64)
-    float2 w[9];
+    // taps: 2D: 9 x f32x2 in registers.  3D: 27 do not fit next to the accumulators; they are staged in shared memory once per
+    // CTA and read per plane (LDS.64).  (Measured: reading the 2D taps from shared memory as well brings the kernel to 64
+    // registers and 4 CTAs / SM, but it is 10 % slower: the kernel is bound by issue slots and the FMA / SFU pipes, not by
+    // latency, see profiles/experiments_r02.md.)
+    float2 wreg[9];
     if constexpr (KT == 1) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) w[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)i * p.C + c_ld));
+        for (int i = 0; i < 9; ++i) wreg[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)i * p.C + c_ld));
     } else {
-        for (int i = tid; i < 27 * kDtCS; i += 256) {
+        for (int i = tid; i < KT * 9 * kDtCS; i += 256) {
             const int tap = i / kDtCS, cc = i - tap * kDtCS;
             s_w[i] = (c_slab + cc < p.C) ? __ldg(p.w + (size_t)tap * p.C + c_slab + cc) : 0.f;
         }
     }
     const uint32_t sw_lane = smem_u32(s_w) + (uint32_t)(2 * lane) * 4u;
+    auto lds_w = [&](int tap) {      // this lane's two channels of one tap
+        if constexpr (KT == 1) {
+            return wreg[tap];
+        } else {
+            float2 r;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(sw_lane + (uint32_t)(tap * kDtCS) * 4u));
+            return r;
+        }
+    };
     const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + c_ld));
     __syncthreads();
     pdl_wait();       // weights above are constants; the input rows below come from the previous kernel
@@ -176,23 +188,19 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
     auto row_s1 = [&](uint32_t srow, int k, float2 (&aOld)[kDtPXW], float2 (&aMid)[kDtPXW], float2 (&aNew)[kDtPXW]) {
 #pragma unroll
         for (int dt = 0; dt < KT; ++dt) {
-            if constexpr (KT == 3) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w[i].x), "=f"(w[i].y) : "r"(sw_lane + (uint32_t)((dt * 9 + i) * kDtCS) * 4u));
-                }
-            }
             float2 v[Cfg::NV];
 #pragma unroll
             for (int i = 0; i < Cfg::NV; ++i) v[i] = dt_lds_half2(srow + (uint32_t)(dt * Cfg::ROWB + i * kDtCS * 2));
 #pragma unroll
-            for (int s = 0; s < 3; ++s)
+            for (int s = 0; s < 3; ++s) {
+                const float2 w0 = lds_w(dt * 9 + s), w1 = lds_w(dt * 9 + 3 + s), w2 = lds_w(dt * 9 + 6 + s);
 #pragma unroll
                 for (int j = 0; j < kDtPXW; ++j) {
-                    aNew[j] = __ffma2_rn(w[0 + s], v[j + s], aNew[j]);
-                    aMid[j] = __ffma2_rn(w[3 + s], v[j + s], aMid[j]);
-                    aOld[j] = __ffma2_rn(w[6 + s], v[j + s], aOld[j]);
+                    aNew[j] = __ffma2_rn(w0, v[j + s], aNew[j]);
+                    aMid[j] = __ffma2_rn(w1, v[j + s], aMid[j]);
+                    aOld[j] = __ffma2_rn(w2, v[j + s], aOld[j]);
                 }
+            }
         }
         if (k >= 2) emit(aOld);
         else {
@@ -229,20 +237,24 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
                 for (int i = 0; i < Cfg::NV; ++i) v[i] = dt_lds_half2(sbase + (uint32_t)(rr * Cfg::ROWB + i * kDtCS * 2));
                 if ((k & 1) == 0) {
 #pragma unroll
-                    for (int s = 0; s < 3; ++s)
+                    for (int s = 0; s < 3; ++s) {
+                        const float2 w6 = lds_w(6 + s), w0 = lds_w(s);
 #pragma unroll
                         for (int j = 0; j < kDtPXW; ++j) {
-                            aX[j] = __ffma2_rn(w[6 + s], v[2 * j + s], aX[j]);     // closes out row k/2 - 1
-                            aY[j] = __ffma2_rn(w[0 + s], v[2 * j + s], aY[j]);     // opens out row k/2
+                            aX[j] = __ffma2_rn(w6, v[2 * j + s], aX[j]);     // closes out row k/2 - 1
+                            aY[j] = __ffma2_rn(w0, v[2 * j + s], aY[j]);     // opens out row k/2
                         }
+                    }
                     if (k > 0) emit(aX);
 #pragma unroll
                     for (int j = 0; j < kDtPXW; ++j) { aX[j] = aY[j]; aY[j] = bias; }
                 } else {
 #pragma unroll
-                    for (int s = 0; s < 3; ++s)
+                    for (int s = 0; s < 3; ++s) {
+                        const float2 w3 = lds_w(3 + s);
 #pragma unroll
-                        for (int j = 0; j < kDtPXW; ++j) aX[j] = __ffma2_rn(w[3 + s], v[2 * j + s], aX[j]);
+                        for (int j = 0; j < kDtPXW; ++j) aX[j] = __ffma2_rn(w3, v[2 * j + s], aX[j]);
+                    }
                 }
             }
         }
@@ -251,6 +263,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
     }
 
     // ---- SE squeeze: fixed-order sum of the 8 column strips, one plain store per channel per CTA ----
+    __syncthreads();                  // every warp is done reading the ring (s_part aliases it)
     s_part[warp * kDtCS + 2 * lane] = lsum.x;
     s_part[warp * kDtCS + 2 * lane + 1] = lsum.y;
     __syncthreads();

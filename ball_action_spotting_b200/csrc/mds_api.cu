@@ -462,15 +462,36 @@ static int launch_dw(const __half* in, __half* out, const float* w, const float*
 static int launch_se(const float* partials, int nparts, const float* w1, const float* b1, const float* w2t, const float* b2,
                      __half* gate, const float* w32, __half* wg, int n, int C, int rd, int N, float inv_count, cudaStream_t st) {
     if (n <= 0) return MDS_OK;
-    if (C > 4096 || rd > 256 || C % 8) return fail(MDS_ERR_INVALID, "se_fc: C must be a multiple of 8, C <= 4096, rd <= 256");
+    if (C > 4096 || rd > 64 || C % 8) return fail(MDS_ERR_INVALID, "se_fc: C must be a multiple of 8, C <= 4096, rd <= 64");
     if (n > 65535 || nparts <= 0) return fail(MDS_ERR_INVALID, "se_fc: bad n / nparts");
     SeParams p;
     p.partials = partials; p.nparts = nparts; p.w1 = w1; p.b1 = b1; p.w2t = w2t; p.b2 = b2; p.gate = gate;
     p.w32 = w32; p.wg = (w32 != nullptr) ? wg : nullptr; p.C = C; p.rd = rd; p.N = N; p.inv_count = inv_count;
-    const int gps = ((C >> 3) + kSeSlices - 1) / kSeSlices;
-    const size_t smem = (size_t)(C + ((rd + 3) & ~3) + gps * 8) * sizeof(float);
+    const size_t smem = se_smem_bytes(C, rd);
+    if (smem > 227 * 1024) return fail(MDS_ERR_INVALID, "se_fc: C=%d rd=%d need %zu bytes of shared memory", C, rd, smem);
+    {
+        static size_t smem_set[kMaxDevices] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < kMaxDevices && smem > smem_set[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(se_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[dev] = smem;
+        }
+    }
     ProfScope ps(MDS_KIND_SE_FC, st);
-    launch_pdl(se_fc_kernel, dim3(n, kSeSlices), dim3(kSeThreads), smem, st, p);
+    {   // one cluster of kSeSlices CTAs per image (+ programmatic stream serialization)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(kSeSlices, n); cfg.blockDim = dim3(kSeThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kSeSlices; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_pdl ? 2 : 1;
+        cudaLaunchKernelEx(&cfg, se_fc_kernel, p);
+    }
     LAUNCH_CHECK("se_fc");
     return MDS_OK;
 }

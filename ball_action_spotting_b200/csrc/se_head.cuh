@@ -5,8 +5,14 @@
 namespace mds {
 
 // gate[n][c] = sigmoid(W2 . SiLU(W1 . mean + b1) + b2), mean = sums / count  (timm SqueezeExcite; multidim_stacker.py:86-90).
-// grid = (images, kSeSlices): every CTA recomputes the tiny squeeze FC, then owns one slice of the channels: it writes
-// their gates and — when wg != nullptr — the slice's columns of this image's gated projection weights
+// The kernel is a chain of latencies, not bandwidth, so it is built to make the chain short:
+//   * one thread-block CLUSTER of 8 CTAs per image; CTA r owns hidden units [r U, r U + U) of the squeeze FC and one
+//     eighth of the channels of the excitation FC; the 8 x U hidden values are exchanged through distributed shared memory
+//     (one DSMEM store per peer + one cluster barrier), so no CTA recomputes the squeeze FC;
+//   * everything that does not depend on the depthwise kernel — this CTA's rows of W1 and its slice of W2 — is staged in
+//     shared memory by cp.async BEFORE griddepcontrol.wait, i.e. while the depthwise kernel is still draining; after the
+//     wait only the partial sums (one round trip) and the fp32 projection weights are read from L2.
+// When wg != nullptr the CTA also writes its slice of this image's gated projection weights
 //     wg[n][o][c] = fp16( w32[o][c] * gate[c] )          (fp32 product, ONE rounding)
 // which the tcgen05 projection GEMM consumes through a 3-D tensor map.  The squeeze is deterministic: the depthwise
 // kernel leaves one partial sum per CTA and they are added here in a fixed order (no float atomics anywhere on the
@@ -26,18 +32,61 @@ struct SeParams {
 };
 
 constexpr int kSeThreads = 512;
-constexpr int kSeSlices = 8;
-constexpr int kSeUnits = 3;          // hidden units a warp accumulates concurrently (rd <= 48 -> one pass)
+constexpr int kSeSlices = 8;          // = cluster size
+__host__ __device__ inline int se_units(int rd) { return (rd + kSeSlices - 1) / kSeSlices; }        // hidden units per CTA
+__host__ __device__ inline int se_slice(int C) { return (((C >> 3) + kSeSlices - 1) / kSeSlices) * 8; }   // channels per CTA
+__host__ __device__ inline size_t se_smem_bytes(int C, int rd) {
+    return (size_t)(se_units(rd) * C + rd * se_slice(C) + C + ((rd + 3) & ~3) + se_slice(C)) * sizeof(float);
+}
+
+__device__ __forceinline__ uint32_t se_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void se_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a float into the shared memory of CTA `rank` of this cluster at the same offset as local address `saddr`
+__device__ __forceinline__ void se_st_cluster(uint32_t saddr, uint32_t rank, float v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(saddr), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
-    extern __shared__ float s_se[];
-    float* s_mean = s_se;            // [C]
-    float* s_hid = s_se + p.C;       // [rd]
-    float* s_gate = s_hid + ((p.rd + 3) & ~3);   // [slice width]
+    extern __shared__ __align__(16) float s_se[];
+    const int U = se_units(p.rd), SW = se_slice(p.C);
+    float* s_w1 = s_se;                          // [U][C]   rows rank*U .. of W1
+    float* s_w2 = s_w1 + U * p.C;                // [rd][SW] this CTA's channel slice of W2^T
+    float* s_mean = s_w2 + p.rd * SW;            // [C]
+    float* s_hid = s_mean + p.C;                 // [rd] (all hidden units, filled by the 8 CTAs of the cluster)
+    float* s_gate = s_hid + ((p.rd + 3) & ~3);   // [SW]
     pdl_trigger();
+    const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)se_cluster_rank();     // == blockIdx.x
+    const int c_lo = min(p.C, rank * SW), c_hi = min(p.C, c_lo + SW);
+    const int sw = c_hi - c_lo;                  // may be 0 for the last ranks of narrow layers
+    const int u_lo = rank * U;
+
+    // ---- constants -> shared memory, before the dependency on the depthwise kernel ----
+    {
+        const int c4n = p.C >> 2;
+        for (int i = tid; i < U * c4n; i += kSeThreads) {
+            const int u = i / c4n, c4 = i - u * c4n;
+            if (u_lo + u < p.rd) cp_async16(s_w1 + u * p.C + c4 * 4, p.w1 + (size_t)(u_lo + u) * p.C + c4 * 4, 16);
+        }
+        const int s4n = sw >> 2;
+        for (int i = tid; i < p.rd * s4n; i += kSeThreads) {
+            const int j = i / s4n, c4 = i - j * s4n;
+            cp_async16(s_w2 + j * SW + c4 * 4, p.w2t + (size_t)j * p.C + c_lo + c4 * 4, 16);
+        }
+        cp_async_commit();
+    }
     pdl_wait();
-    const int n = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- squeeze: fixed-order sum of the depthwise kernel's partials (all loads of a thread in flight together) ----
     const float* part = p.partials + (size_t)n * p.nparts * p.C;
-    for (int c = tid; c < p.C; c += kSeThreads) {      // fixed summation order; 4 loads in flight per step
+    for (int c = tid; c < p.C; c += kSeThreads) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int q = 0;
         for (; q + 3 < p.nparts; q += 4) {
@@ -47,62 +96,39 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
         for (; q < p.nparts; ++q) a0 += __ldg(part + (size_t)q * p.C + c);
         s_mean[c] = ((a0 + a1) + (a2 + a3)) * p.inv_count;
     }
+    cp_async_wait<0>();
     __syncthreads();
-    // squeeze FC: each warp owns up to kSeUnits hidden units and walks the channels ONCE for all of them, so their
-    // weight loads are in flight together (the kernel is a chain of L2 latencies, not bandwidth)
-    {
-        constexpr int kWarps = kSeThreads / 32;
+    // ---- squeeze FC: warp u -> hidden unit u_lo + u (U <= 8 warps busy), result broadcast to every CTA of the cluster ----
+    if (warp < U && u_lo + warp < p.rd) {
         const float4* m = reinterpret_cast<const float4*>(s_mean);
-        const int c4n = p.C >> 2;
-        for (int j0 = warp; j0 < p.rd; j0 += kWarps * kSeUnits) {
-            float acc[kSeUnits];
-            const float4* wrow[kSeUnits];
-#pragma unroll
-            for (int u = 0; u < kSeUnits; ++u) {
-                acc[u] = 0.f;
-                const int j = j0 + u * kWarps;
-                wrow[u] = reinterpret_cast<const float4*>(p.w1 + (size_t)(j < p.rd ? j : j0) * p.C);
-            }
-#pragma unroll 3
-            for (int c = lane; c < c4n; c += 32) {
-                const float4 mv = m[c];
-#pragma unroll
-                for (int u = 0; u < kSeUnits; ++u) {
-                    const float4 wv = __ldg(wrow[u] + c);
-                    acc[u] = fmaf(wv.x, mv.x, fmaf(wv.y, mv.y, fmaf(wv.z, mv.z, fmaf(wv.w, mv.w, acc[u]))));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kSeUnits; ++u) {
-                const int j = j0 + u * kWarps;
-                const float a = warp_sum(acc[u]);
-                if (lane == 0 && j < p.rd) s_hid[j] = silu_f(a + __ldg(p.b1 + j));
-            }
+        const float4* wr = reinterpret_cast<const float4*>(s_w1 + warp * p.C);
+        float acc = 0.f;
+        for (int c4 = lane; c4 < (p.C >> 2); c4 += 32) {
+            const float4 mv = m[c4], wv = wr[c4];
+            acc = fmaf(wv.x, mv.x, fmaf(wv.y, mv.y, fmaf(wv.z, mv.z, fmaf(wv.w, mv.w, acc))));
         }
+        acc = warp_sum(acc);
+        const int j = u_lo + warp;
+        const float hv = silu_f(acc + __ldg(p.b1 + j));
+        if (lane < kSeSlices) se_st_cluster(smem_u32(s_hid + j), (uint32_t)lane, hv);
     }
-    __syncthreads();
-    // this CTA's channel slice, in units of 8 channels (16 bytes of fp16)
-    const int groups = p.C >> 3, gps = (groups + kSeSlices - 1) / kSeSlices;
-    const int c_lo = min(p.C, slice * gps * 8), c_hi = min(p.C, c_lo + gps * 8);
-    // expand FC + sigmoid: 4 lanes per channel split the hidden units, so each lane has rd/4 independent loads
-    for (int c0 = c_lo; c0 < c_hi; c0 += kSeThreads / 4) {
-        const int c = c0 + (tid >> 2), sub = tid & 3;
-        float a = 0.f;
-        if (c < c_hi) {
-#pragma unroll 4
-            for (int j = sub; j < p.rd; j += 4) a = fmaf(__ldg(p.w2t + (size_t)j * p.C + c), s_hid[j], a);
+    se_cluster_sync();            // all hidden units of the image are in every CTA's s_hid
+    // ---- excitation FC + sigmoid for this CTA's channel slice ----
+    for (int cc = tid; cc < sw; cc += kSeThreads) {
+        float a0 = 0.f, a1 = 0.f;
+        int j = 0;
+        for (; j + 1 < p.rd; j += 2) {
+            a0 = fmaf(s_w2[j * SW + cc], s_hid[j], a0);
+            a1 = fmaf(s_w2[(j + 1) * SW + cc], s_hid[j + 1], a1);
         }
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        if (c < c_hi && sub == 0) {
-            const float gv = sigmoid_f(a + __ldg(p.b2 + c));
-            s_gate[c - c_lo] = gv;
-            p.gate[(size_t)n * p.C + c] = __float2half_rn(gv);
-        }
+        if (j < p.rd) a0 = fmaf(s_w2[j * SW + cc], s_hid[j], a0);
+        const float gv = sigmoid_f(a0 + a1 + __ldg(p.b2 + c_lo + cc));
+        s_gate[cc] = gv;
+        p.gate[(size_t)n * p.C + c_lo + cc] = __float2half_rn(gv);
     }
-    if (p.wg == nullptr) return;
+    if (p.wg == nullptr || sw == 0) return;
     __syncthreads();
-    const int wgrp = (c_hi - c_lo) >> 3;                 // 8-channel groups in this slice
+    const int wgrp = sw >> 3;                            // 8-channel groups in this slice
     __half* wg = p.wg + (size_t)n * p.N * p.C;
     const int total = p.N * wgrp;
     auto gate8 = [&](int i, const float4& x0, const float4& x1) {
@@ -117,23 +143,20 @@ __global__ void __launch_bounds__(kSeThreads) se_fc_kernel(SeParams p) {
         const int o = i / wgrp, gq = i - o * wgrp;
         return reinterpret_cast<const float4*>(p.w32 + (size_t)o * p.C + c_lo + gq * 8);
     };
-    int i = tid;
-    for (; i + 3 * kSeThreads < total; i += 4 * kSeThreads) {  // four items (eight 16-byte loads) in flight per thread: this loop is a
-        const float4* s0 = src(i);                             // chain of L2 round trips, so its time is the number of trips
-        const float4* s1 = src(i + kSeThreads);
-        const float4* s2 = src(i + 2 * kSeThreads);
-        const float4* s3 = src(i + 3 * kSeThreads);
-        const float4 a0 = __ldg(s0), a1 = __ldg(s0 + 1), b0 = __ldg(s1), b1 = __ldg(s1 + 1);
-        const float4 c0 = __ldg(s2), c1 = __ldg(s2 + 1), d0 = __ldg(s3), d1 = __ldg(s3 + 1);
-        gate8(i, a0, a1);
-        gate8(i + kSeThreads, b0, b1);
-        gate8(i + 2 * kSeThreads, c0, c1);
-        gate8(i + 3 * kSeThreads, d0, d1);
-    }
-    for (; i < total; i += kSeThreads) {
-        const float4* s0 = src(i);
-        const float4 a0 = __ldg(s0), a1 = __ldg(s0 + 1);
-        gate8(i, a0, a1);
+    // four items (eight 16-byte loads) in flight per thread, also in the last, partial round: the loop is a chain of L2 round
+    // trips, so its time is the number of rounds
+    for (int i = tid; i < total; i += 4 * kSeThreads) {
+        float4 x[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int it = i + q * kSeThreads;
+            if (it < total) { const float4* s0 = src(it); x[q][0] = __ldg(s0); x[q][1] = __ldg(s0 + 1); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int it = i + q * kSeThreads;
+            if (it < total) gate8(it, x[q][0], x[q][1]);
+        }
     }
 }
 
