@@ -100,17 +100,64 @@ class _FrameGraphs:
         self._ws = eng._ws          # the recorded launches point into this workspace: keep it alive if the engine grows a new one
         self.version = eng.version  # weights (and gem_p, a kernel argument) are baked into the recording
 
-    def encode(self, frames) -> torch.Tensor:
-        for i, f in enumerate(frames):
-            self.frames[i].copy_(f)
-        self.g2d.replay()
-        return self.feat.clone()
 
-    def head(self, feats) -> torch.Tensor:
-        for j, f in enumerate(feats):
-            self.stack[:, j].copy_(f)
-        self.g3d.replay()
-        return self.pred.clone()
+class _Rings:
+    """Device-resident state of the streaming predictor: the reference keeps two Python dicts of
+    tensors (predictors.py:33-48); here the live window is a ring of uint8 frames and a ring of fp16 triple features, both
+    allocated once, addressed by ``index % size`` and validated by a host-side tag per slot (so out-of-order indices behave
+    like the reference's dict lookups).  Nothing is allocated per frame."""
+    OUT_SLOTS = 64
+
+    def __init__(self, predictor: "MultiDimStackerPredictor", h: int, w: int):
+        dev = predictor.device
+        W, H = predictor.image_size
+        gen = predictor.indexes_generator
+        span = (predictor.model_stack_size - 1) * predictor.frame_stack_step          # frames a triple reaches past its start
+        self.nf = gen.behind + gen.ahead + 1                                           # 29 live frames for 15 x 2
+        self.nt = self.nf - span                                                       # 25 live triple starts
+        n_tta = 2 if predictor.tta else 1
+        self.frames = torch.zeros((self.nf, h, w), dtype=torch.uint8, device=dev)
+        self.feats = torch.zeros((n_tta, self.nt, H // 32, W // 32, 192), dtype=torch.float16, device=dev)
+        self.out = torch.zeros((self.OUT_SLOTS, predictor.num_classes), dtype=torch.float32, device=dev)
+        self.reset()
+        self.calls = 0
+
+    def reset(self):
+        self.frame_tag = [None] * self.nf
+        self.triple_tag = [None] * self.nt
+
+    def clear_old(self, minimum_index: int):
+        """predictors.py:38-44: drop frames older than the window and triples that contain one."""
+        self.frame_tag = [t if (t is not None and t >= minimum_index) else None for t in self.frame_tag]
+        self.triple_tag = [t if (t is not None and t >= minimum_index) else None for t in self.triple_tag]
+
+    def put_frame(self, frame: torch.Tensor, index: int):
+        self.frames[index % self.nf].copy_(frame)
+        self.frame_tag[index % self.nf] = index
+
+    def has_frame(self, index: int) -> bool:
+        return self.frame_tag[index % self.nf] == index
+
+    def frame(self, index: int) -> torch.Tensor:
+        return self.frames[index % self.nf]
+
+    def has_triple(self, start: int) -> bool:
+        return self.triple_tag[start % self.nt] == start
+
+    def put_triple(self, start: int, feat: torch.Tensor):
+        self.feats[:, start % self.nt].copy_(feat)
+        self.triple_tag[start % self.nt] = start
+
+    def triple(self, start: int) -> torch.Tensor:
+        return self.feats[:, start % self.nt]
+
+    def emit(self, pred: torch.Tensor) -> torch.Tensor:
+        """The result of call k lives in slot k % OUT_SLOTS of a rotating buffer (valid for the next 63 calls; the reference
+        script copies it to the host immediately, scripts/ball_action/predict.py:48)."""
+        o = self.out[self.calls % self.OUT_SLOTS]
+        o.copy_(pred)
+        self.calls += 1
+        return o
 
 
 class MultiDimStackerPredictor:
@@ -119,6 +166,7 @@ class MultiDimStackerPredictor:
         self.model = load_model(model_path, device=device, bias_correction=bias_correction)
         self.cuda_graph = cuda_graph
         self._graphs: Optional[_FrameGraphs] = None
+        self._rings: Optional[_Rings] = None
         self.model.eval()
         self.device = self.model.device
         self.tta = tta
@@ -131,20 +179,12 @@ class MultiDimStackerPredictor:
         self.frame_stack_step = self.model.params["frame_stack_step"]
         self.indexes_generator = StackIndexesGenerator(self.frame_stack_size, self.frame_stack_step)
         self.model_stack_size = self.model.params["nn_module"][1]["stack_size"]
-
-        self._frame_index2frame: dict = dict()
-        self._stack_indexes2features: dict = dict()
+        self.num_classes = self.model.params["nn_module"][1]["num_classes"]
         self._predict_offset: int = self.indexes_generator.make_stack_indexes(0)[-1]
 
     def reset_buffers(self):
-        self._frame_index2frame = dict()
-        self._stack_indexes2features = dict()
-
-    def _clear_old(self, minimum_index: int):
-        for index in [i for i in self._frame_index2frame if i < minimum_index]:
-            del self._frame_index2frame[index]
-        for stack_indexes in [s for s in self._stack_indexes2features if any(i < minimum_index for i in s)]:
-            del self._stack_indexes2features[stack_indexes]
+        if self._rings is not None:
+            self._rings.reset()
 
     def _encode(self, eng, frames: torch.Tensor) -> torch.Tensor:
         """frames (3, h, W) uint8 -> cached features (n_tta, fh, fw, 192) fp16 (predictors.py:60-66; the TTA flip is the
@@ -169,23 +209,37 @@ class MultiDimStackerPredictor:
         frame = frame.to(device=self.device)
         if frame.dtype != torch.uint8:
             raise RuntimeError("predict() takes the raw uint8 frame (frames.py normalisation is fused on the GPU)")
-        self._frame_index2frame[index] = frame.contiguous()
+        if self._rings is None or self._rings.frames.shape[-2:] != frame.shape[-2:]:
+            self._rings = _Rings(self, frame.shape[-2], frame.shape[-1])
+        rings = self._rings
         predict_index = index - self._predict_offset
         predict_indexes = self.indexes_generator.make_stack_indexes(predict_index)
-        self._clear_old(predict_indexes[0])
-        if set(predict_indexes) <= set(self._frame_index2frame.keys()):
+        rings.clear_old(predict_indexes[0])                                # predictors.py:56
+        rings.put_frame(frame, index)                                      # :53 (a frame older than the window is dropped below)
+        if index < predict_indexes[0]:
+            rings.frame_tag[index % rings.nf] = None
+        if all(rings.has_frame(i) for i in predict_indexes):               # :57
             eng = self.model.nn_module.engine(self.device)
             if self.cuda_graph and (self._graphs is None or self._graphs.frames.shape[-2:] != frame.shape[-2:]
                                     or self._graphs.version != eng.version):        # re-packed weights invalidate the recording
                 self._graphs = _FrameGraphs(self, frame.shape[-2], frame.shape[-1])
-            stacks_indexes = list(batched(predict_indexes, self.model_stack_size))
-            for stack_indexes in stacks_indexes:
-                if stack_indexes not in self._stack_indexes2features:
-                    triple = [self._frame_index2frame[i] for i in stack_indexes]
-                    self._stack_indexes2features[stack_indexes] = (
-                        self._graphs.encode(triple) if self.cuda_graph else self._encode(eng, torch.stack(triple, dim=0)))
-            cached = [self._stack_indexes2features[s] for s in stacks_indexes]     # T x (n_tta, fh, fw, 192)
+            g = self._graphs
+            starts = [s[0] for s in batched(predict_indexes, self.model_stack_size)]          # T triple starts (:58)
+            for s in starts:
+                if not rings.has_triple(s):                                                    # :59-67
+                    triple = [rings.frame(s + k * self.frame_stack_step) for k in range(self.model_stack_size)]
+                    if self.cuda_graph:
+                        for k, f in enumerate(triple):
+                            g.frames[k].copy_(f)
+                        g.g2d.replay()
+                        rings.put_triple(s, g.feat)
+                    else:
+                        rings.put_triple(s, self._encode(eng, torch.stack(triple, dim=0)))
             if self.cuda_graph:
-                return self._graphs.head(cached), predict_index
-            return self._head(eng, torch.stack(cached, dim=1).contiguous()), predict_index
+                for j, s in enumerate(starts):                                                 # torch.cat of the cached features (:68)
+                    g.stack[:, j].copy_(rings.triple(s))
+                g.g3d.replay()
+                return rings.emit(g.pred), predict_index
+            window = torch.stack([rings.triple(s) for s in starts], dim=1)
+            return rings.emit(self._head(eng, window)), predict_index
         return None, predict_index

@@ -187,3 +187,52 @@ def test_sweep_assembles_the_same_windows_as_the_streaming_predictor(tta):
         assert torch.allclose(got[j], want, rtol=1e-5, atol=1e-3), (p, got[j], want)
     with pytest.raises(RuntimeError, match="need frames"):
         sweep.predict_range(frames, first_frame, 110, 120)                                   # halo outside the buffer
+
+
+def test_predictor_rings_follow_the_reference_dict_semantics():
+    """predictor._Rings (device rings addressed by index % size + host tags) against the reference's two dicts
+    (src/predictors.py:33-48, 53-67): same 'window complete' decisions and the same cache misses, frame by frame,
+    including a reset and a jump in the frame index."""
+    from types import SimpleNamespace
+    from ball_action_spotting_b200.indexes import StackIndexesGenerator
+    from ball_action_spotting_b200.predictor import _Rings, batched
+    gen = StackIndexesGenerator(15, 2)
+    fake = SimpleNamespace(device=torch.device("cpu"), image_size=(64, 32), indexes_generator=gen, model_stack_size=3,
+                           frame_stack_step=2, tta=True, num_classes=2)
+    rings = _Rings(fake, 30, 64)
+    assert (rings.nf, rings.nt) == (29, 25) and rings.feats.shape == (2, 25, 1, 2, 192)
+    frames_d, triples_d = {}, {}
+    seq = list(range(0, 70)) + list(range(500, 560))          # a jump: everything cached becomes stale
+    for index in seq:
+        p = index - 14
+        idx = gen.make_stack_indexes(p)
+        frames_d[index] = True                                                    # reference: predictors.py:53-56
+        for k in [k for k in frames_d if k < idx[0]]:
+            del frames_d[k]
+        for k in [k for k in triples_d if any(i < idx[0] for i in k)]:
+            del triples_d[k]
+        ref_ready = set(idx) <= set(frames_d)
+        ref_miss = []
+        if ref_ready:
+            for tr in batched(idx, 3):
+                if tr not in triples_d:
+                    triples_d[tr] = True
+                    ref_miss.append(tr[0])
+        rings.clear_old(idx[0])                                                   # ours
+        rings.put_frame(torch.full((30, 64), index % 251, dtype=torch.uint8), index)
+        ready = all(rings.has_frame(i) for i in idx)
+        miss = []
+        if ready:
+            for tr in batched(idx, 3):
+                if not rings.has_triple(tr[0]):
+                    rings.put_triple(tr[0], torch.full((2, 1, 2, 192), float(tr[0] % 100), dtype=torch.float16))
+                    miss.append(tr[0])
+            for tr in batched(idx, 3):                                            # slots hold what was stored for that triple
+                assert float(rings.triple(tr[0])[0, 0, 0, 0]) == float(tr[0] % 100)
+            assert int(rings.frame(idx[0])[0, 0]) == idx[0] % 251
+        assert ready == ref_ready and miss == ref_miss, (index, miss, ref_miss)
+    assert miss == [idx[12]]                                   # steady state: one new triple per frame (SURVEY.md 3.2)
+    rings.reset()
+    assert not any(rings.has_frame(i) for i in range(560))
+    o1, o2 = rings.emit(torch.tensor([0.25, 0.75])), rings.emit(torch.tensor([0.5, 0.5]))
+    assert o1.tolist() == [0.25, 0.75] and o2.tolist() == [0.5, 0.5]              # rotating output slots do not alias
