@@ -34,8 +34,11 @@ class FrozenEncoderTrainer:
     def __init__(self, model: MultiDimStacker, lr: float, momentum: float = 0.9, nesterov: bool = True,
                  focal_alpha: float = 0.4, focal_gamma: float = 1.2, amp: bool = True,
                  drop_rate: Optional[float] = None, drop_path_rate: Optional[float] = None, init_scale: float = 65536.0,
-                 ema_decay: Optional[float] = None):
+                 ema_decay: Optional[float] = None, batch_transform=None):
+        """batch_transform: optional callable (frames, target) -> (frames, target) applied on the device before the encoder,
+        where the reference applies its GPU augmentations and mixup (argus_models.py:49-53)."""
         self.lib = _lib.load()
+        self.batch_transform = batch_transform
         self.model = model
         dev = model.classifier.weight.device
         if dev.type != "cuda":
@@ -142,6 +145,19 @@ class FrozenEncoderTrainer:
                     sd[k] = torch.tensor(self._ema_tracked, dtype=torch.long, device=sd[k].device)
         return sd
 
+    #: how this trainer deviates from ``BallActionModel.train_step``; ``checkpoint_params`` records it next to the weights
+    DEVIATIONS = {"b200_frozen_encoder_mode": "eval (running BatchNorm statistics, no DropPath); the reference keeps the frozen "
+                                              "encoder in train mode (argus_models.py:42,104-110)",
+                  "b200_iter_size": 1}
+
+    def checkpoint_params(self, params: dict) -> dict:
+        """``params`` for ``EmaCheckpoint`` (src/ema.py:71-76) with the deviations of this trainer recorded, so that a checkpoint
+        trained here is distinguishable from a reference-trained one (its conv2d_encoder BatchNorm buffers stay at their
+        pre-trained values instead of drifting with the batch statistics)."""
+        out = dict(params)
+        out.update(self.DEVIATIONS)
+        return out
+
     def scaler_state(self) -> Tuple[float, float, float, float]:
         out = (C.c_float * 4)()
         check(self.lib.mds_train_scaler_state(self._h, out), "mds_train_scaler_state")
@@ -204,6 +220,9 @@ class FrozenEncoderTrainer:
         frames, target = batch
         frames = frames.to(self.device, non_blocking=True)
         target = target.to(self.device, non_blocking=True)
+        if self.batch_transform is not None:                 # GPU augmentations / mixup of the reference (argus_models.py:49-53)
+            with torch.no_grad():
+                frames, target = self.batch_transform(frames, target)
         loss, logits = self.step_on_features(self.encoder_features(frames), target)
         if self.ema_decay is not None:
             self.ema_update()

@@ -1,16 +1,14 @@
-"""GPU: distribution of the end-to-end error over 16 random full-size stacks, and the staged tensors at full size.
+"""GPU: the end-to-end error over 16 random full-size stacks, and the staged tensors at full size.
 
-north_star: logits within 1e-3 relative (max|got - ref| / max|ref|) of the fp32 CPU forward.  The engine stores activations
-and GEMM weights in fp16 (BASELINE.json configs[1]); a CPU emulation of exactly those roundings on the fp32 oracle
-(tests/precision_study.py, DESIGN.md "Numerics") gives an RMS logit error of 3.7e-4..4.5e-4 of max|logit| on these
-random-weight networks, i.e. single stacks land anywhere between 1e-4 and ~1.4e-3.  This file therefore asserts what the
-fp16 format can hold for EVERY input, with nothing scaled by the test:
-  * RMS over the 16 stacks            <= 6e-4      (measured 4.5e-4)
-  * every stack                       <= 2e-3      (measured max 1.35e-3)
-  * at least 12 of the 16 stacks      <= 1e-3      (measured 14)
-and records how many stacks meet the 1e-3 bar in gpurun_out/parity_report.jsonl ("sweep16.*").  The fixed-input full-size
-cases in test_e2e_gpu.py are held to 1e-3 unscaled.  forward_2d / forward_3d have no pooling after them; their
-full-size errors are recorded and held to the emulation's prediction for un-pooled tensors (1e-2)."""
+north_star: logits within 1e-3 relative (max|got - ref| / max|ref|) of the fp32 CPU forward, asserted here UNSCALED on every
+one of the 16 stacks, on the logits and on the sigmoid probabilities.  The engine stores activations and GEMM weights in fp16
+(BASELINE.json configs[1]); a CPU emulation of exactly those roundings on the fp32 oracle (tests/precision_study.py, DESIGN.md
+"Numerics") predicts an RMS logit error of ~4e-4 of max|logit| on these random-weight networks, so the 1e-3 bound sits at about
+2.4 sigma: this build measures RMS 4.2e-4, max 9.7e-4 (16 of 16 stacks within 1e-3); the forward is bit-reproducible, so the
+outcome is a fixed property of the build, and a kernel change that moves any stack past 1e-3 fails this test.  The per-stack
+values are written to gpurun_out/parity_report.jsonl ("sweep16.*").
+forward_2d / forward_3d have no pooling after them; their full-size errors are recorded and held to 1e-3 RMS / 1e-2 max
+(the emulation's prediction for un-pooled tensors of a random-weight network)."""
 import json
 from pathlib import Path
 
@@ -56,11 +54,11 @@ def test_sixteen_random_full_size_stacks(oracle_sd):
     perr = (torch.sigmoid(got) - torch.sigmoid(ref)).abs()
     rms, mx, within = err.pow(2).mean().sqrt().item(), err.max().item(), int((per_stack <= 1e-3).sum())
     record("sweep16.logits_rms", rms, 6e-4)
-    record("sweep16.logits_max", mx, 2e-3)
-    record("sweep16.stacks_within_1e-3_of_16", within, 12)
-    record("sweep16.probs_max", perr.max().item(), 2e-3)
+    record("sweep16.logits_max", mx, 1e-3)
+    record("sweep16.stacks_within_1e-3_of_16", within, 16)
+    record("sweep16.probs_max", perr.max().item(), 1e-3)
     record("sweep16.per_stack_max", [round(v, 6) for v in per_stack.tolist()], 1e-3)
-    assert rms <= 6e-4 and mx <= 2e-3 and within >= 12 and perr.max().item() <= 2e-3, (rms, mx, within, per_stack.tolist())
+    assert mx <= 1e-3 and perr.max().item() <= 1e-3 and rms <= 6e-4, (rms, mx, within, per_stack.tolist())
     # the same stacks one by one and in one batch of 16: every kernel is batch-invariant, so the logits are bit-identical
     one = torch.cat([net(u8[i:i + 1].to(DEV)).cpu() for i in range(4)])
     assert torch.equal(one, got[:4])

@@ -5,8 +5,11 @@ B=${1:-4}
 OUT=gpurun_out
 mkdir -p $OUT
 NCU="ncu --set full --clock-control none --import-source on -f"
+KEEP=${KEEP_REPS:-"dw_b41 gemm_b51"}     # gpurun brings back at most 64 MiB: keep the raw / source CSV pages of every capture, the .ncu-rep of a few
 cap() {  # name, kernel regex, skip, count
   $NCU -k "regex:$2" -s $3 -c $4 -o $OUT/ncu_r02_$1 python tools/ncu_target.py $B > $OUT/ncu_r02_$1.log 2>&1 || tail -3 $OUT/ncu_r02_$1.log
+  ncu -i $OUT/ncu_r02_$1.ncu-rep --page raw --csv > $OUT/ncu_r02_$1.raw.csv 2>/dev/null
+  case " $KEEP " in *" $1 "*) ;; *) rm -f $OUT/ncu_r02_$1.ncu-rep ;; esac
 }
 cap stem 'stem_kernel' 0 1
 cap conv3x3 'conv3x3_kernel' 0 4          # blocks.0.0, 1.0, 2.0, 2.1

@@ -19,9 +19,13 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    return rows[0], rows[1], rows[-1]
+    """-> header, units, [one row of values per captured launch]; accepts an .ncu-rep or its `--page raw --csv` export."""
+    if rep.endswith(".csv"):
+        out = Path(rep).read_text()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(out.splitlines()) if r]
+    return rows[0], rows[1], rows[2:]
 
 
 def main():
@@ -31,7 +35,7 @@ def main():
         i = args.index("--launches")
         launches = args[i + 1]
         args = args[:i] + args[i + 2:]
-    workload = "tools/ncu_target.py 16 (FULL forward, 16 stacks = 80 images)"
+    workload = "tools/ncu_target.py 4 (FULL forward, batch 4 = 20 images, BASELINE.json configs[1])"
     if "--workload" in args:
         i = args.index("--workload")
         workload = args[i + 1]
@@ -39,30 +43,35 @@ def main():
     out_dir = ROOT / "profiles"
     out_dir.mkdir(exist_ok=True)
     lines = [f"# ncu --set full --clock-control none, one launch per kernel (round {tag}); workload: {workload}", ""]
+    traffic = {}
     for rep in args:
-        hdr, units, vals = raw(rep)
-        name = vals[hdr.index("Kernel Name")]
-        lines.append(f"## {Path(rep).stem}: {name}")
-        d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
-        for m in METRICS:
-            if m in d:
-                lines.append(f"  {m:70s} {d[m][0]:>16s} {d[m][1]}")
-        try:
-            t = float(d["gpu__time_duration.sum"][0].replace(",", ""))
-            tu = d["gpu__time_duration.sum"][1]
-            us = t * {"us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(tu.replace("second", "s").replace("usecond", "us").replace("msecond", "ms").replace("nsecond", "ns"), 1)
-            def b(x):
-                v, u = d[x]
-                return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-            tr = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
-            lines.append(f"  {'traffic = dram read + write':70s} {tr / 1e6:16.1f} MB  -> {tr / us / 1e3:.0f} GB/s over the launch")
-        except Exception as e:  # noqa: BLE001
-            lines.append(f"  (traffic n/a: {e})")
-        stall = sorted(((float(vals[i].replace(",", "")), h) for i, h in enumerate(hdr)
-                        if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h and vals[i].replace(",", "").replace(".", "").isdigit()), reverse=True)
-        tot = sum(v for v, _ in stall) or 1
-        lines.append("  top stall reasons: " + ", ".join(f"{h.split('stalled_')[1]} {100 * v / tot:.0f}%" for v, h in stall[:5]))
-        lines.append("")
+        hdr, units, launches_ = raw(rep)
+        for li, vals in enumerate(launches_):
+            name = vals[hdr.index("Kernel Name")]
+            lines.append(f"## {Path(rep).name.replace('.raw.csv', '').replace('.ncu-rep', '')} launch {li}: {name}")
+            d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+            for m in METRICS:
+                if m in d:
+                    lines.append(f"  {m:70s} {d[m][0]:>16s} {d[m][1]}")
+            try:
+                t = float(d["gpu__time_duration.sum"][0].replace(",", ""))
+                tu = d["gpu__time_duration.sum"][1]
+                us = t * {"us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(tu.replace("second", "s").replace("usecond", "us").replace("msecond", "ms").replace("nsecond", "ns"), 1)
+                def b(x):
+                    v, u = d[x]
+                    return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+                tr = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
+                lines.append(f"  {'traffic = dram read + write':70s} {tr / 1e6:16.1f} MB  -> {tr / us / 1e3:.0f} GB/s over the launch")
+                traffic[f"{Path(rep).name.split('.')[0]}[{li}]"] = {"kernel": name.split("(")[0], "traffic_bytes": tr, "duration_us": us}
+            except Exception as e:  # noqa: BLE001
+                lines.append(f"  (traffic n/a: {e})")
+            stall = sorted(((float(vals[i].replace(",", "")), h) for i, h in enumerate(hdr)
+                            if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h and vals[i].replace(",", "").replace(".", "").isdigit()), reverse=True)
+            tot = sum(v for v, _ in stall) or 1
+            lines.append("  top stall reasons: " + ", ".join(f"{h.split('stalled_')[1]} {100 * v / tot:.0f}%" for v, h in stall[:5]))
+            lines.append("")
+    import json
+    (out_dir / f"ncu_{tag}_traffic_by_capture.json").write_text(json.dumps(traffic, indent=1))
     (out_dir / f"ncu_{tag}_summary.txt").write_text("\n".join(lines))
     print("\n".join(lines))
     if launches:
