@@ -378,21 +378,27 @@ static int launch_gemm_tc_stream(const __half* A, const __half* Wg, const __half
     return tc_launch(tmA, tmB, tmBias, p, st);
 }
 
-// bias_mat: [N][64] fp16, column 0 = fp16(bias), column 1 = fp16(bias - column 0), rest 0 (packer.py); enables the tcgen05 path
+// bias_mat: [N][64] fp16, column 0 = fp16(bias), column 1 = fp16(bias - column 0), rest 0 (packer.py): the tcgen05 path.
+// The forward passes ONLY run the tcgen05 kernel: a shape outside its limits is an error, not a silent switch to another
+// kernel.  legacy = true (training GEMMs with a residual and N > 256; the mds_k_gemm1x1 cross-check entry) selects the
+// mma.sync kernel of gemm1x1.cuh explicitly.
 static int launch_gemm(const __half* A, const __half* W, const float* bias, const __half* res, const __half* gate,
                        __half* C, long long rows_per_img, int n_img, int N, int K, int act, cudaStream_t st,
-                       const __half* bias_mat = nullptr) {
+                       const __half* bias_mat = nullptr, bool legacy = false) {
     if (K % 16 || N % 16 || K > 1152) return fail(MDS_ERR_INVALID, "gemm1x1: N, K must be multiples of 16, K <= 1152 (N=%d K=%d)", N, K);
     if (rows_per_img <= 0 || n_img <= 0) return MDS_OK;
     if (bias_mat != nullptr && gate == nullptr && res == nullptr && K <= kTcMaxKB * kTcBK && rows_per_img * n_img < (1LL << 31) && tc_pick_bn(N) >= 32)
         return launch_gemm_tc(A, W, bias_mat, C, rows_per_img * n_img, N, K, act, st);
+    if (!legacy)
+        return fail(MDS_ERR_INVALID, "gemm: N=%d K=%d (gate %d, residual %d) is outside the tcgen05 kernel's limits (ungated, K <= %d, "
+                    "N a multiple of 64..256)", N, K, gate != nullptr, res != nullptr, kTcMaxKB * kTcBK);
     // The M-tile index lives in gridDim.y (<= 65535): split very large ungated problems into row slabs.
     const long long max_rows = 65535LL * kGemmBM;
     if (gate == nullptr && rows_per_img * n_img > max_rows) {
         long long total = rows_per_img * n_img;
         for (long long r0 = 0; r0 < total; r0 += max_rows) {
             long long rows = total - r0 < max_rows ? total - r0 : max_rows;
-            TRY(launch_gemm(A + r0 * K, W, bias, res ? res + r0 * N : nullptr, nullptr, C + r0 * N, rows, 1, N, K, act, st));
+            TRY(launch_gemm(A + r0 * K, W, bias, res ? res + r0 * N : nullptr, nullptr, C + r0 * N, rows, 1, N, K, act, st, nullptr, true));
         }
         return MDS_OK;
     }
@@ -1256,7 +1262,7 @@ extern "C" int mds_k_gemm1x1(const void* A, const void* W, const float* bias, co
     return launch_gemm(reinterpret_cast<const __half*>(A), reinterpret_cast<const __half*>(W), bias,
                        reinterpret_cast<const __half*>(res), reinterpret_cast<const __half*>(gate),
                        reinterpret_cast<__half*>(C), rows_per_img, n_img, N, K, act, reinterpret_cast<cudaStream_t>(stream),
-                       reinterpret_cast<const __half*>(bias_mat));
+                       reinterpret_cast<const __half*>(bias_mat), true);
 }
 extern "C" int mds_k_dwconv(const void* in, void* out, const float* w, const float* bias, float* partials, int* nparts, int n,
                             int T, int H, int W, int C, int kt, int stride, void* stream) {

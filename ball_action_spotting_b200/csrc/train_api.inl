@@ -303,7 +303,7 @@ static int train_gemm(MdsTrainer* t, const __half* A, const __half* W, const __h
         return launch_gemm(A, W, t->zeros, nullptr, nullptr, C, M, 1, N, K, 0, st, t->zeros16);
     if (N >= 32 && N <= 256 && N % 16 == 0 && K % 16 == 0 && M < (1LL << 31))
         return launch_gemm_tc_stream(A, W, t->zeros16, res, C, (int)M, 1, N, K, 0, st);
-    return launch_gemm(A, W, t->zeros, res, nullptr, C, M, 1, N, K, 0, st);
+    return launch_gemm(A, W, t->zeros, res, nullptr, C, M, 1, N, K, 0, st, nullptr, true);      // mma.sync kernel, explicitly
 }
 
 // rows per CTA of the column kernels: about four CTAs per SM in total, so that the grid is whole waves at 2 CTAs / SM

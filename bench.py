@@ -357,7 +357,8 @@ def run_b200(args):
             how = "depthwise + SE items of the fused tail kernels, projection items off (mds_set_tail_dw_only)"
         else:
             ms2, ms3 = by_kind["dwconv2d"]["ms_per_step"], by_kind["dwconv3d"]["ms_per_step"]
-            how = "dwconv_tma kernels (depthwise + squeeze + SE MLP of the last CTA)" if args.tail_mode == 2 else "round-1 dwconv kernels"
+            how = {3: "dwconv_tma kernels (TMA-staged depthwise + squeeze partials)", 2: "dwconv_tma kernels (depthwise + squeeze + SE MLP of the last CTA)",
+                   0: "round-1 cp.async dwconv kernels"}[args.tail_mode]
         g2 = dwb["dwconv2d"] * B / (ms2 / 1e3) / 1e9 if ms2 > 0 else 0.0
         g3 = dwb["dwconv3d"] * B / (ms3 / 1e3) / 1e9 if ms3 > 0 else 0.0
         roofline_dw = {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["src"],
