@@ -145,6 +145,14 @@ extern "C" int mds_set_tail_mode(int mode) {
     g_tail_mode = mode;
     return MDS_OK;
 }
+// Encoder (mds_forward, mds_forward_2d) as S equal parts of the images on S streams (default 2), see forward_2d_streams
+constexpr int kMaxStreams = 4;
+static int g_streams = getenv("MDS_STREAMS") ? atoi(getenv("MDS_STREAMS")) : 2;
+extern "C" int mds_set_streams(int n) {
+    if (n < 1 || n > kMaxStreams) return fail(MDS_ERR_INVALID, "streams must be in 1..%d", kMaxStreams);
+    g_streams = n;
+    return MDS_OK;
+}
 // measurement only (bench.py roofline_dw): 1 = the fused tails run their depthwise + SE items alone (outputs are NOT valid)
 static bool g_tail_dw_only = false;
 extern "C" int mds_set_tail_dw_only(int enabled) { g_tail_dw_only = enabled != 0; return MDS_OK; }
@@ -757,6 +765,8 @@ struct MdsHandle {
     float gem_p = 3.0f;
     const float *cls_w = nullptr, *cls_b = nullptr;
     int* sync = nullptr;          // [3][kSyncSlots] inter-CTA words of the fused MBConv tail; zero between launches
+    cudaStream_t aux_stream[kMaxStreams - 1] = {};      // extra streams of the multi-stream encoder (mds_set_streams)
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams - 1] = {};
     int T() const { return cfg.num_frames / cfg.stack_size; }
     int mid3d() const { return cfg.num_3d_features * cfg.expansion_3d_ratio; }
     int rd3d() const { return mid3d() / cfg.se_reduce_3d_ratio; }
@@ -800,6 +810,11 @@ extern "C" int mds_create(const MdsConfig* cfg, MdsHandle** out) {
         DeviceGuard g(cfg->device);
         cudaError_t e = cudaMalloc(&h->sync, 3 * kSyncSlots * sizeof(int));
         if (e == cudaSuccess) e = cudaMemset(h->sync, 0, 3 * kSyncSlots * sizeof(int));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+        for (int i = 0; i < kMaxStreams - 1 && e == cudaSuccess; ++i) {
+            e = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+        }
         if (e != cudaSuccess) { delete h; return fail(MDS_ERR_CUDA, "mds_create: %s", cudaGetErrorString(e)); }
     }
     *out = h;
@@ -811,6 +826,11 @@ extern "C" int mds_destroy(MdsHandle* h) {
     DeviceGuard g(h->cfg.device);
     for (auto& kv : h->tensors) cudaFree(kv.second.ptr);
     cudaFree(h->sync);
+    for (int i = 0; i < kMaxStreams - 1; ++i) {
+        if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     return MDS_OK;
 }
@@ -987,7 +1007,13 @@ extern "C" size_t mds_workspace_bytes(const MdsHandle* h, int H, int W, int n_im
     if (!h) return 0;
     const int P = (H / 32) * (W / 32);
     const size_t rows = (size_t)n_stacks * h->T() * P;
-    size_t full = ws2d_bytes(h, H, W, n_images) + al256(rows * 192 * 2) + ws3d_bytes(h, n_stacks, P) +
+    size_t w2d = ws2d_bytes(h, H, W, n_images);
+    for (int S = 2; S <= kMaxStreams && S <= n_images; ++S) {        // multi-stream encoder: each part of the images has its own scratch
+        size_t parts = 0;
+        for (int k = 0; k < S; ++k) parts += ws2d_bytes(h, H, W, n_images / S + (k < n_images % S ? 1 : 0));
+        if (parts > w2d) w2d = parts;
+    }
+    size_t full = w2d + al256(rows * 192 * 2) + ws3d_bytes(h, n_stacks, P) +
                   al256(rows * h->cfg.num_3d_stack_proj * 2) + wshead_bytes(h, n_stacks);
     return full + 4096;
 }
@@ -1079,6 +1105,38 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
     return MDS_OK;
 }
 
+// forward_2d over one stream or, when mds_set_streams(S >= 2), as S equal parts of the images on S streams, each with its own
+// scratch: the images are independent, and the kernels of one part fill the ramps and tails of the others (measured +1.8 % at
+// batch 4, +1.1 % at batch 32 for S = 2; 3 and 4 are slower).  Results are bit-identical: every kernel is batch-invariant.
+static int forward_2d_streams(MdsHandle* h, const MdsFrames& frames, int n_images, __half* feats, Arena& ar, cudaStream_t st) {
+    const int S = g_streams < n_images ? g_streams : n_images;
+    // long buffers (the sweep: thousands of images in chunk_images passes) keep the machine full on one stream: measured 2 % slower there
+    if (S < 2 || n_images > 2 * h->cfg.chunk_images || !(g_tail_mode == 0 || g_tail_mode == 3) || g_prof_on)
+        return forward_2d_impl(h, frames, n_images, feats, ar, st);
+    const int P = (frames.H / 32) * (frames.W / 32);
+    CUDA_TRY(cudaEventRecord(h->ev_fork, st));
+    size_t off = ar.off;
+    int i0 = 0;
+    for (int k = 0; k < S; ++k) {
+        const int nk = n_images / S + (k < n_images % S ? 1 : 0);
+        const size_t wk = ws2d_bytes(h, frames.H, frames.W, nk);
+        if (off + wk > ar.cap) return fail(MDS_ERR_WORKSPACE, "forward_2d: workspace too small for the %d-stream encoder", S);
+        Arena ak(ar.base + off, wk);
+        off += wk;
+        MdsFrames fk = frames;
+        fk.data = reinterpret_cast<const char*>(frames.data) + (size_t)i0 * frames.img_stride * (frames.dtype == 0 ? 1 : 4);
+        cudaStream_t sk = k == 0 ? st : h->aux_stream[k - 1];
+        if (k > 0) CUDA_TRY(cudaStreamWaitEvent(sk, h->ev_fork, 0));
+        TRY(forward_2d_impl(h, fk, nk, feats + (size_t)i0 * P * 192, ak, sk));
+        if (k > 0) {
+            CUDA_TRY(cudaEventRecord(h->ev_join[k - 1], sk));
+            CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join[k - 1], 0));
+        }
+        i0 += nk;
+    }
+    return MDS_OK;
+}
+
 static int forward_3d_impl(MdsHandle* h, const __half* feats, int b, int fh, int fw, __half* out, Arena& ar, cudaStream_t st) {
     if (b <= 0) return MDS_OK;
     if (fh <= 0 || fw <= 0) return fail(MDS_ERR_INVALID, "forward_3d: bad feature map size %dx%d", fh, fw);
@@ -1153,7 +1211,7 @@ extern "C" int mds_forward_2d(MdsHandle* h, const MdsFrames* frames, int n_image
     if (!frames || !frames->data || !feats_out || !ws) return fail(MDS_ERR_INVALID, "forward_2d: null argument");
     DeviceGuard g(h->cfg.device);
     Arena ar(ws, ws_bytes);
-    return forward_2d_impl(h, *frames, n_images, reinterpret_cast<__half*>(feats_out), ar, reinterpret_cast<cudaStream_t>(stream));
+    return forward_2d_streams(h, *frames, n_images, reinterpret_cast<__half*>(feats_out), ar, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mds_forward_encoder(MdsHandle* h, const MdsFrames* frames, int n_images, void* feats_out, void* ws,
@@ -1198,7 +1256,7 @@ extern "C" int mds_forward(MdsHandle* h, const MdsFrames* frames, int b, float* 
     __half* feats = ar.take<__half>(rows * 192);
     __half* out3d = ar.take<__half>(rows * h->cfg.num_3d_stack_proj);
     if (ar.overflow) return fail(MDS_ERR_WORKSPACE, "forward: workspace too small");
-    TRY(forward_2d_impl(h, *frames, b * T, feats, ar, st));
+    TRY(forward_2d_streams(h, *frames, b * T, feats, ar, st));
     // the 2D scratch is dead now: re-use the arena from the same mark for the 3D stage
     Arena ar3(ar.base + al256(rows * 192 * 2) + al256(rows * h->cfg.num_3d_stack_proj * 2),
               ws_bytes - al256(rows * 192 * 2) - al256(rows * h->cfg.num_3d_stack_proj * 2));

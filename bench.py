@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--tta", type=int, default=0)
     ap.add_argument("--tail-mode", type=int, default=3, choices=[0, 1, 2, 3],
                     help="MBConv tails: 3 = TMA depthwise + SE kernel + GEMM (default), 2 = depthwise+SE kernel and gating GEMM, 1 = one fused launch, 0 = round-1 path")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 3, 4], help="encoder on one stream or as equal parts of the images on several streams (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
     a = ap.parse_args()
@@ -191,6 +192,7 @@ def run_b200(args):
     net.to(dev).eval()
     eng = net.engine(dev)
     eng.lib.mds_set_tail_mode(args.tail_mode)
+    eng.lib.mds_set_streams(args.streams)
 
     # synthetic uint8 frames; R rotating batches so that consecutive steps never re-read the same input from L2
     bytes_in = B * FRAMES * STORED_H * W
@@ -401,6 +403,7 @@ def run_b200(args):
                 "gpu_launches": launches,
                 "bias_correction": bool(net._bias_correction),
                 "roofline": roofline, "roofline_dw": roofline_dw, "roofline_by_kind": by_kind, "cpu_baseline": cpu_baseline,
+                "encoder_streams": args.streams,
                 "mbconv_tail": {2: "dwconv_tma (depthwise + SE) + gating GEMM: 2 launches", 1: "mbconv_tail: 1 launch",
                                 0: "round-1 path: dwconv + se_fc + gated GEMM: 3 launches",
                                 3: "dwconv_tma + se_fc + pre-gated GEMM: 3 launches"}[args.tail_mode]}

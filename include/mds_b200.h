@@ -239,6 +239,9 @@ int mds_set_pdl(int enabled);
  * 2: mds_k_dwconv_se (incl. the SE MLP) + mds_k_gemm_gate; 1: mds_k_mbconv_tail (ONE persistent launch);
  * 0: round-1 path mds_k_dwconv + mds_k_se_fc + mds_k_gemm_gated. */
 int mds_set_tail_mode(int mode);
+/* The encoder of mds_forward / mds_forward_2d runs as n equal parts of the images on n streams (default 2: the kernels of one half
+ * fill the ramps and tails of the other; handle-owned streams forked from / joined to the caller's stream; 1 = single stream). */
+int mds_set_streams(int n);
 /* Measurement only (bench.py `roofline_dw`): 1 = the fused tails execute their depthwise + SE items alone, so that the
  * depthwise stage can be timed by itself; forward outputs are NOT valid while this is set. */
 int mds_set_tail_dw_only(int enabled);
