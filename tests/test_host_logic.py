@@ -236,3 +236,18 @@ def test_predictor_rings_follow_the_reference_dict_semantics():
     assert not any(rings.has_frame(i) for i in range(560))
     o1, o2 = rings.emit(torch.tensor([0.25, 0.75])), rings.emit(torch.tensor([0.5, 0.5]))
     assert o1.tolist() == [0.25, 0.75] and o2.tolist() == [0.5, 0.5]              # rotating output slots do not alias
+
+
+def test_accounting_is_consistent_across_tail_modes():
+    """accounting.py feeds bench.py's roofline: the launch lists of the MBConv-tail schemes must describe the same work."""
+    from ball_action_spotting_b200 import accounting as acc
+    t3, t1 = acc.per_stack_totals(tail_mode=2), acc.per_stack_totals(tail_mode=1)
+    t0 = acc.per_stack_totals(tail_mode=0)
+    flops = lambda t: sum(v["flops"] for v in t.values())
+    assert abs(flops(t3) - flops(t1)) < 1e-6 * flops(t3) and abs(flops(t3) - flops(t0)) < 1e-6 * flops(t3)
+    assert abs(flops(t3) / 141.6e9 - 1) < 0.01                                  # SURVEY.md 8(d): 141.6 GFLOP per stack
+    assert t0["se_fc"]["launches"] == 20 and "se_fc" not in t3 and t1["tail2d"]["launches"] == 16 and t1["tail3d"]["launches"] == 4
+    dw = acc.depthwise_only_bytes()
+    assert abs(dw["dwconv2d"] / (5 * 102.3e6) - 1) < 0.01 and abs(dw["dwconv3d"] / 42.4e6 - 1) < 0.01   # SURVEY 8(d) DW-only bytes
+    # one launch of every encoder kernel per image chunk: 1 stem + 5 conv3x3 + 16 x (pw, dw, se, pwl) + proj = 71 (mode 0)
+    assert len(acc.encoder_launches(736, 1280, 720, tail_mode=0)) == 71 and len(acc.encoder_launches(736, 1280, 720, tail_mode=1)) == 39
