@@ -83,6 +83,7 @@ SIGNATURES = {
     "mds_set_pdl": (_i, [_i]),
     "mds_set_tail_mode": (_i, [_i]),
     "mds_set_streams": (_i, [_i]),
+    "mds_set_conv_mode": (_i, [_i]),
     "mds_set_tail_dw_only": (_i, [_i]),
     "mds_launch_count": (C.c_longlong, [_i]),
     "mds_profile_begin": (_i, []),

@@ -1,0 +1,396 @@
+// K2 (+K3) on the 5th-gen tensor cores, every dense 3x3 block of the encoder:
+//   ConvBnAct    (timm blocks.0.0):                 y = SiLU(conv3x3(x) * s + b)
+//   EdgeResidual (timm blocks.1.0 / 1.1 / 2.0):     y = conv1x1( SiLU( conv3x3_stride(x) * s1 + b1 ) ) * s2 + b2 (+ x)
+// as ONE persistent, warp-specialised tcgen05 kernel (reference call site: multidim_stacker.py:166-176, the timm blocks
+// it builds).  The expanded tensor never leaves the SM, and with PT = true it never leaves TENSOR MEMORY: the SiLU
+// epilogue writes it back to TMEM as packed fp16 (tcgen05.st) and the projection MMA takes its A operand from there.
+//
+// Implicit GEMM without im2col.  The halo tile is loaded by TMA as 8-channel PLANES, plane[c8][pixel][8 ch], pixels in
+// row-major order of the tile (5-D tensor map over NHWC seen as [n][C/8][H][W][8]; hardware zero fill = the conv padding).
+// In the no-swizzle K-major UMMA layout a row is 16 bytes and 8-row groups are 128 bytes apart, so "row m of the A
+// operand" is "pixel p0 + m of the linearised tile" and a tap of the stencil is only a start-address offset.
+//   stride 1: one plane set of (TW+2) x (TH+2) pixels; tap (r, s) = offset r * (TW+2) + s; 2 garbage rows of M per tile row
+//   stride 2: the input is read as its four (row parity, column parity) PHASES, each a dense (TW+1) x (TH+1) image
+//             (four tensor maps with element strides doubled and the base moved by one row / pixel; TF-SAME on even sizes
+//             pads bottom / right only = TMA zero fill); tap (r, s) = phase (r&1, s&1) at offset (r>>1)*(TW+1) + (s>>1)
+//   warp 0 / lane 0 : TMA producer (double-buffered halo tiles)
+//   warp 1 / lane 0 : MMA issuer: per 128-pixel M tile 9 x CIN/16 tcgen05.mma (N = CMID) + one against a "ones" tile that
+//                     adds the bias; later CMID/16 MMAs (N = CPROJ) for the projection
+//   other warps     : epilogue, two ping-pong groups: TMEM -> SiLU -> fp16 -> TMEM / smem (A operand of the projection);
+//                     then TMEM -> + residual -> fp16 -> 32-byte global stores
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv3x3_tc.cuh"
+#include "gemm_tc.cuh"
+
+namespace mds {
+
+struct ConvTcMaps { CUtensorMap m[4]; };     // stride 1: m[0]; stride 2: phase (py, px) = m[py * 2 + px]
+
+struct ConvTcParams {
+    const __half* in;     // [n][H][W][CIN]  (also the residual)
+    __half* out;          // [n][Ho][Wo][COUT],  COUT = CPROJ ? CPROJ : CMID
+    const __half* w1;     // [CMID][9*CIN]   k = (r*3+s)*CIN + ci, BN folded
+    const float* b1;      // [CMID]
+    const __half* w2;     // [CPROJ][CMID]
+    const float* b2;      // [CPROJ]
+    int n, H, W, Ho, Wo;
+    int tiles_x, tiles_y;
+};
+
+template <int CIN, int CMID, int CPROJ, int STRIDE, bool RES, int TH_, bool PT>
+struct ConvTcCfg {
+    static constexpr int TW = 32, TH = TH_;
+    static constexpr int NPH = STRIDE == 1 ? 1 : 4;
+    static constexpr int PW = STRIDE == 1 ? TW + 2 : TW + 1;
+    static constexpr int PH = STRIDE == 1 ? TH + 2 : TH + 1;
+    static constexpr int PIX = PW * PH;                          // pixels per plane
+    static constexpr int PLANE = PIX * 16;                       // bytes per 8-channel plane
+    static constexpr int PHASE_BYTES = (CIN / 8) * PLANE;
+    static constexpr int TILE_BYTES = NPH * PHASE_BYTES;
+    static constexpr int MT_MAX = (TH * PW + 127) / 128;         // M tiles of 128 linear pixels
+    static constexpr int MAX_OFF = STRIDE == 1 ? 2 * PW + 2 : PW + 1;
+    static constexpr int OVER = MT_MAX * 128 + MAX_OFF > PIX ? MT_MAX * 128 + MAX_OFF - PIX : 0;   // pixels the last M tile over-reads
+    static constexpr int TILE_ALLOC = ((TILE_BYTES + OVER * 16 + 127) / 128) * 128;
+    static constexpr int HALVES = CMID >= 32 ? 2 : 1;            // epilogue warps that share a TMEM lane quadrant and accumulator
+    static constexpr int EPI_WARPS = 8 * HALVES;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int W1_BYTES = 9 * CIN * CMID * 2;          // [tap][c8][n][8]
+    static constexpr int W2_BYTES = CMID * CPROJ * 2;            // [c8][n][8]
+    static constexpr int P_BYTES = (CPROJ > 0 && !PT) ? 128 * CMID * 2 : 0;   // [c8][row][8], one per accumulator
+    static constexpr int ONES_BYTES = 2 * 128 * 16;              // [2 planes][128 rows][8]: (row, k=0,1) = 1
+    static constexpr int BM1_BYTES = 2 * CMID * 16;              // [2 planes][CMID][8]: (n, k=0,1) = bias hi/lo
+    static constexpr int BM2_BYTES = 2 * CPROJ * 16;
+    // tensor memory columns: D1[2] | P[2] (packed fp16, PT only) | D2[2]
+    static constexpr int D1_STRIDE = CMID < 32 ? 32 : CMID;
+    static constexpr int P_COL = 2 * D1_STRIDE;
+    static constexpr int D2_COL = P_COL + (CPROJ > 0 ? CMID : 0);
+    static constexpr int D2_STRIDE = 64;
+    static constexpr int TMEM_USED = D2_COL + (CPROJ > 0 ? 2 * D2_STRIDE : 0);
+    static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    static constexpr size_t SMEM = 128 + 2 * (size_t)TILE_ALLOC + W1_BYTES + W2_BYTES + 2 * P_BYTES + ONES_BYTES + BM1_BYTES +
+                                   BM2_BYTES + 256;
+    static_assert(CIN % 16 == 0 && CMID % 16 == 0 && CPROJ % 16 == 0, "channel counts must be multiples of 16");
+    static_assert(!RES || (STRIDE == 1 && CPROJ == CIN), "residual needs same shape");
+    static_assert(PHASE_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
+    static_assert(TMEM_USED <= 512, "TMEM columns");
+    static_assert(CPROJ <= 64, "projection accumulator stride");
+    static_assert(SMEM <= 232448, "shared memory");
+};
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int CIN, int CMID, int CPROJ, int STRIDE, bool RES, int TH_, bool PT, int MINB>
+__global__ void __launch_bounds__((ConvTcCfg<CIN, CMID, CPROJ, STRIDE, RES, TH_, PT>::THREADS), MINB)
+conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, ConvTcParams p) {
+    using Cfg = ConvTcCfg<CIN, CMID, CPROJ, STRIDE, RES, TH_, PT>;
+    constexpr int NT = Cfg::THREADS;
+    constexpr int COUT = CPROJ ? CPROJ : CMID;
+    constexpr bool PROJ = CPROJ > 0;
+    extern __shared__ unsigned char ctc_smem_raw[];
+    pdl_trigger();
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ctc_smem_raw) + 127) & ~uintptr_t(127));
+    unsigned char* s_tile = smem;                                   // [2][TILE_ALLOC]
+    unsigned char* s_w1 = s_tile + 2 * Cfg::TILE_ALLOC;             // [9][CIN/8][CMID][16 B]
+    unsigned char* s_w2 = s_w1 + Cfg::W1_BYTES;                     // [CMID/8][CPROJ][16 B]
+    unsigned char* s_p = s_w2 + Cfg::W2_BYTES;                      // [2][CMID/8][128][16 B]   (PT = false)
+    unsigned char* s_ones = s_p + 2 * Cfg::P_BYTES;
+    unsigned char* s_bm1 = s_ones + Cfg::ONES_BYTES;
+    unsigned char* s_bm2 = s_bm1 + Cfg::BM1_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bm2 + Cfg::BM2_BYTES);
+    uint64_t* tile_full = bars;          // [2]
+    uint64_t* tile_empty = bars + 2;     // [2]
+    uint64_t* d1_full = bars + 4;        // [2]
+    uint64_t* d1_empty = bars + 6;       // [2]
+    uint64_t* p_full = bars + 8;         // [2]
+    uint64_t* d2_full = bars + 10;       // [2]
+    uint64_t* d2_empty = bars + 12;      // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int ntiles = tiles_per_img * p.n;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 1);
+            mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], Cfg::EPI_WARPS / 2);
+            mbar_init(&p_full[i], Cfg::EPI_WARPS / 2);
+            mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], Cfg::EPI_WARPS / 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < Cfg::NPH; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
+    }
+    // ---- weights, ones tile and bias tiles -> smem in the no-swizzle K-major plane layout (once per CTA) ----
+    for (int i = tid; i < 9 * (CIN / 8) * CMID; i += NT) {                  // dest chunk (tap, c8, n)
+        const int nrow = i % CMID, pl = i / CMID;                            // pl = tap * (CIN/8) + c8
+        reinterpret_cast<uint4*>(s_w1)[i] = __ldg(reinterpret_cast<const uint4*>(p.w1 + (size_t)nrow * 9 * CIN + pl * 8));
+    }
+    if constexpr (PROJ) {
+        for (int i = tid; i < (CMID / 8) * CPROJ; i += NT) {
+            const int nrow = i % CPROJ, c8 = i / CPROJ;
+            reinterpret_cast<uint4*>(s_w2)[i] = __ldg(reinterpret_cast<const uint4*>(p.w2 + (size_t)nrow * CMID + c8 * 8));
+        }
+        for (int i = tid; i < 2 * CPROJ; i += NT) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (i < CPROJ) {
+                const float b = __ldg(p.b2 + i);
+                const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
+                v.x = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+            }
+            reinterpret_cast<uint4*>(s_bm2)[i] = v;
+        }
+    }
+    for (int i = tid; i < 2 * 128; i += NT)
+        reinterpret_cast<uint4*>(s_ones)[i] = (i < 128) ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 2 * CMID; i += NT) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i < CMID) {
+            const float b = __ldg(p.b1 + i);
+            const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
+            v.x = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+        }
+        reinterpret_cast<uint4*>(s_bm1)[i] = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    pdl_wait();       // on-chip set-up done; activations (and the output buffer) belong to earlier kernels until now
+
+    auto tile_geom = [&](int tile, int& n, int& y0, int& x0, int& nm) {
+        n = tile / tiles_per_img;
+        const int rem = tile - n * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        y0 = ty * Cfg::TH; x0 = tx * Cfg::TW;                    // output coordinates
+        const int rows = min(Cfg::TH, p.Ho - y0);
+        nm = (rows * Cfg::PW + 127) / 128;                       // M tiles that contain valid output pixels
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int i = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+                int n, y0, x0, nm;
+                tile_geom(tile, n, y0, x0, nm);
+                const int buf = i & 1;
+                mbar_wait(&tile_empty[buf], (((uint32_t)i >> 1) & 1) ^ 1);
+                mbar_expect_tx(&tile_full[buf], (uint32_t)Cfg::TILE_BYTES);
+                unsigned char* dst = s_tile + (size_t)buf * Cfg::TILE_ALLOC;
+                if constexpr (STRIDE == 1) {
+                    tma_load_5d(dst, &maps.m[0], &tile_full[buf], 0, x0 - 1, y0 - 1, 0, n);
+                } else {
+#pragma unroll
+                    for (int ph = 0; ph < 4; ++ph)
+                        tma_load_5d(dst + (size_t)ph * Cfg::PHASE_BYTES, &maps.m[ph], &tile_full[buf], 0, x0, y0, 0, n);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc1 = tc_idesc(128, CMID);
+            const uint32_t w1a = smem_u32(s_w1), onesa = smem_u32(s_ones);
+            const uint64_t ones_desc = tc_desc_nosw(onesa, 128 * 16);
+            const uint64_t bm1_desc = tc_desc_nosw(smem_u32(s_bm1), CMID * 16);
+            auto mma2 = [&](int u) {             // projection of M tile u: D2 = P . W2^T + b2
+                if constexpr (PROJ) {
+                    const uint32_t idesc2 = tc_idesc(128, CPROJ);
+                    const uint32_t w2a = smem_u32(s_w2);
+                    const uint64_t bm2_desc = tc_desc_nosw(smem_u32(s_bm2), CPROJ * 16);
+                    const int a = u & 1;
+                    const uint32_t ph = ((uint32_t)u >> 1) & 1;
+                    mbar_wait(&p_full[a], ph);
+                    mbar_wait(&d2_empty[a], ph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d2 = tmem_base + Cfg::D2_COL + a * Cfg::D2_STRIDE;
+                    tc_mma_f16(d2, ones_desc, bm2_desc, idesc2, 0);
+#pragma unroll
+                    for (int kk = 0; kk < CMID / 16; ++kk) {
+                        const uint64_t bdesc = tc_desc_nosw(w2a + kk * 2 * (CPROJ * 16), CPROJ * 16);
+                        if constexpr (PT) {
+                            tc_mma_f16_ts(d2, tmem_base + Cfg::P_COL + a * (CMID / 2) + kk * 8, bdesc, idesc2, 1);
+                        } else {
+                            tc_mma_f16(d2, tc_desc_nosw(smem_u32(s_p) + a * Cfg::P_BYTES + kk * 2 * (128 * 16), 128 * 16), bdesc, idesc2, 1);
+                        }
+                    }
+                    tc_commit(&d2_full[a]);
+                }
+            };
+            int i = 0, t = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+                int n, y0, x0, nm;
+                tile_geom(tile, n, y0, x0, nm);
+                const int buf = i & 1;
+                mbar_wait(&tile_full[buf], ((uint32_t)i >> 1) & 1);
+                tc_fence_after();
+                const uint32_t ta = smem_u32(s_tile + (size_t)buf * Cfg::TILE_ALLOC);
+                for (int m = 0; m < nm; ++m, ++t) {
+                    const int a = t & 1;
+                    mbar_wait(&d1_empty[a], (((uint32_t)t >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d1 = tmem_base + a * Cfg::D1_STRIDE;
+                    tc_mma_f16(d1, ones_desc, bm1_desc, idesc1, 0);                     // D1 = bias
+#pragma unroll
+                    for (int rs = 0; rs < 9; ++rs) {
+                        const int r = rs / 3, s = rs - r * 3;
+                        const int phase = STRIDE == 1 ? 0 : (r & 1) * 2 + (s & 1);
+                        const int off = STRIDE == 1 ? r * Cfg::PW + s : (r >> 1) * Cfg::PW + (s >> 1);
+                        const uint32_t a_addr = ta + (uint32_t)(phase * Cfg::PHASE_BYTES) + (uint32_t)(m * 128 + off) * 16u;
+#pragma unroll
+                        for (int kc = 0; kc < CIN / 16; ++kc)
+                            tc_mma_f16(d1, tc_desc_nosw(a_addr + kc * 2 * Cfg::PLANE, Cfg::PLANE),
+                                       tc_desc_nosw(w1a + (rs * (CIN / 8) + kc * 2) * (CMID * 16), CMID * 16), idesc1, 1);
+                    }
+                    tc_commit(&d1_full[a]);
+                    if (t >= 1) mma2(t - 1);
+                }
+                tc_commit(&tile_empty[buf]);            // every MMA that reads this halo tile has been issued
+            }
+            if (t >= 1) mma2(t - 1);
+        }
+    } else {
+        // ================= epilogue: two groups of 4 * HALVES warps =================
+        const int q = warp & 3;                         // TMEM lane quadrant
+        const int e = ((warp - 2) >> 2) & 1;            // group = accumulator index
+        const int half = (warp - 2) >> 3;               // which part of the columns (0 when HALVES == 1)
+        const int row = q * 32 + lane;                  // row of the M tile = linear tile pixel
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        int i = 0, t = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+            int n, y0, x0, nm;
+            tile_geom(tile, n, y0, x0, nm);
+            for (int m = 0; m < nm; ++m, ++t) {
+                if ((t & 1) != e) continue;
+                const uint32_t ph = ((uint32_t)t >> 1) & 1;
+                const int lp = m * 128 + row;                                    // linear pixel inside the row-major tile
+                const int ry = lp / Cfg::PW, cx = lp - ry * Cfg::PW;
+                const int oy = y0 + ry, ox = x0 + cx;
+                const bool ok = (cx < Cfg::TW) && (ry < Cfg::TH) && (oy < p.Ho) && (ox < p.Wo);
+                const size_t pix = ((size_t)n * p.Ho + (ok ? oy : 0)) * p.Wo + (ok ? ox : 0);
+
+                // ---- epilogue 1: D1 -> SiLU -> fp16 -> P (A operand of the projection) or, without projection, global ----
+                mbar_wait(&d1_full[e], ph);
+                tc_fence_after();
+                constexpr int G1 = CMID / 16 / Cfg::HALVES;      // 16-column groups per warp
+                constexpr int GC = G1 >= 2 ? 2 : 1;              // groups in flight
+#pragma unroll
+                for (int g0 = 0; g0 < G1; g0 += GC) {
+                    uint32_t v[GC][16];
+#pragma unroll
+                    for (int j = 0; j < GC; ++j) tc_ld16(t_row + (uint32_t)(e * Cfg::D1_STRIDE + (half * G1 + g0 + j) * 16), v[j]);
+                    tc_wait_ld();
+                    if (g0 + GC >= G1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&d1_empty[e]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < GC; ++j) {
+                        const int g = half * G1 + g0 + j;       // columns [16g, 16g+16) = channels = planes 2g, 2g+1
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int h = 0; h < 8; ++h)
+                            pk[h] = pack_half2(silu_f(__uint_as_float(v[j][2 * h])), silu_f(__uint_as_float(v[j][2 * h + 1])));
+                        if constexpr (!PROJ) {
+                            if (ok) st_global_v8(p.out + pix * COUT + g * 16, pk);
+                        } else if constexpr (PT) {
+                            tc_st8(t_row + (uint32_t)(Cfg::P_COL + e * (CMID / 2) + g * 8), pk);
+                        } else {
+                            unsigned char* pbuf = s_p + e * Cfg::P_BYTES;
+                            *reinterpret_cast<uint4*>(pbuf + (size_t)(2 * g) * (128 * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            *reinterpret_cast<uint4*>(pbuf + (size_t)(2 * g + 1) * (128 * 16) + row * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
+                    }
+                }
+                if constexpr (PROJ) {
+                    if constexpr (PT) {
+                        tc_wait_st();
+                        tc_fence_before();
+                    } else {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // P written by the generic proxy, read by tcgen05.mma
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_full[e]);
+
+                    // ---- epilogue 2: D2 (+ residual) -> fp16 -> global ----
+                    constexpr int NG2 = CPROJ / 16;          // 16-column groups: 2 (CPROJ 32) or 3 (CPROJ 48)
+                    // half 0 takes groups 0 and 2, half 1 takes group 1
+                    uint32_t rv[2][8];
+                    if constexpr (RES) {
+                        if (ok) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const int g = half + 2 * j;
+                                if (g < NG2) ld_global_v8(p.in + pix * CIN + g * 16, rv[j]);
+                            }
+                        }
+                    }
+                    mbar_wait(&d2_full[e], ph);
+                    tc_fence_after();
+                    uint32_t v2[2][16];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int g = half + 2 * j;
+                        if (g < NG2) tc_ld16(t_row + (uint32_t)(Cfg::D2_COL + e * Cfg::D2_STRIDE + g * 16), v2[j]);
+                    }
+                    tc_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d2_empty[e]);
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int g = half + 2 * j;
+                            if (g < NG2) {
+                                uint32_t pk[8];
+#pragma unroll
+                                for (int h = 0; h < 8; ++h) {
+                                    float x0f = __uint_as_float(v2[j][2 * h]), x1f = __uint_as_float(v2[j][2 * h + 1]);
+                                    if constexpr (RES) {
+                                        const float2 r2 = unpack_half2(rv[j][h]);
+                                        x0f += r2.x; x1f += r2.y;
+                                    }
+                                    pk[h] = pack_half2(x0f, x1f);
+                                }
+                                st_global_v8(p.out + pix * COUT + g * 16, pk);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace mds

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "conv3x3.cuh"
 #include "conv3x3_tc.cuh"
+#include "conv_tc.cuh"
 #include "dwconv.cuh"
 #include "dwconv_tma.cuh"
 #include "gemm1x1.cuh"
@@ -145,6 +146,16 @@ extern "C" int mds_set_tail_mode(int mode) {
     g_tail_mode = mode;
     return MDS_OK;
 }
+// Dense 3x3 blocks (blocks.0.0 - 2.1), selectable for A/B measurements (all parity-tested):
+//   2 (default): conv_tc_kernel (TMA + tcgen05, expanded tensor kept in tensor memory) for blocks.0.0 / 1.0 / 1.1 / 2.0
+//   1: conv_tc_kernel with the expanded tensor staged in shared memory
+//   0: round-1 kernels (mma.sync conv3x3_kernel; conv3x3_tc_kernel for blocks.1.1)
+static int g_conv_mode = getenv("MDS_CONV_MODE") ? atoi(getenv("MDS_CONV_MODE")) : 2;
+extern "C" int mds_set_conv_mode(int mode) {
+    if (mode < 0 || mode > 2) return fail(MDS_ERR_INVALID, "conv mode must be 0..2");
+    g_conv_mode = mode;
+    return MDS_OK;
+}
 // Encoder (mds_forward, mds_forward_2d) as S equal parts of the images on S streams (default 2), see forward_2d_streams
 constexpr int kMaxStreams = 4;
 static int g_streams = getenv("MDS_STREAMS") ? atoi(getenv("MDS_STREAMS")) : 2;
@@ -249,6 +260,47 @@ static int launch_conv3_tc(const __half* in, __half* out, const __half* w1, cons
     return MDS_OK;
 }
 
+// every dense 3x3 block on tcgen05 (conv_tc.cuh): halo tiles through 5-D tensor maps over NHWC seen as [n][C/8][H][W][8];
+// stride 2 reads the four (row, column) parity phases of the input through four maps
+template <int CIN, int CMID, int CPROJ, int STRIDE, bool RES, int TH, bool PT, int MINB>
+static int launch_conv_tc(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2, const float* b2,
+                          int n, int H, int W, cudaStream_t st) {
+    using Cfg = ConvTcCfg<CIN, CMID, CPROJ, STRIDE, RES, TH, PT>;
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    if (STRIDE == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv_tc: stride-2 input must be even");
+    ConvTcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    for (int ph = 0; ph < Cfg::NPH; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        cuuint64_t dims[5] = {8, (cuuint64_t)(W / STRIDE), (cuuint64_t)(H / STRIDE), (cuuint64_t)(CIN / 8), (cuuint64_t)n};
+        cuuint64_t strides[4] = {(cuuint64_t)STRIDE * CIN * 2, (cuuint64_t)STRIDE * W * CIN * 2, 16, (cuuint64_t)H * W * CIN * 2};
+        cuuint32_t box[5] = {8, (cuuint32_t)Cfg::PW, (cuuint32_t)Cfg::PH, (cuuint32_t)(CIN / 8), 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const __half* base = in + ((size_t)py * W + px) * CIN;
+        CUresult r = enc(&maps.m[ph], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled(conv_tc) failed (%d) n=%d H=%d W=%d C=%d stride=%d", (int)r, n, H, W, CIN, STRIDE);
+    }
+    ConvTcParams p;
+    p.in = in; p.out = out; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.n = n; p.H = H; p.W = W;
+    p.Ho = H / STRIDE; p.Wo = W / STRIDE;
+    p.tiles_x = (p.Wo + Cfg::TW - 1) / Cfg::TW;
+    p.tiles_y = (p.Ho + Cfg::TH - 1) / Cfg::TH;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * n;
+    if (tiles <= 0) return MDS_OK;
+    auto kern = conv_tc_kernel<CIN, CMID, CPROJ, STRIDE, RES, TH, PT, MINB>;
+    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
+    int grid = num_sms() * MINB;
+    if (tiles < grid) grid = (int)tiles;
+    ProfScope ps(MDS_KIND_CONV3X3, st);
+    launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, maps, p);
+    LAUNCH_CHECK("conv_tc");
+    return MDS_OK;
+}
+
 static int launch_conv3(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2,
                         const float* b2, int n, int H, int W, int cin, int cmid, int stride, int cproj, int res,
                         cudaStream_t st) {
@@ -257,6 +309,18 @@ static int launch_conv3(const __half* in, __half* out, const __half* w1, const f
     p.n = n; p.H = H; p.W = W;
     p.Ho = (H + stride - 1) / stride; p.Wo = (W + stride - 1) / stride;
     if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv3x3: stride-2 input must be even");
+    if (g_conv_mode >= 1 && H > 0 && W > 0 && (stride == 1 || (H % 2 == 0 && W % 2 == 0))) {
+        const bool pt = g_conv_mode == 2;
+#define CTCASE(CI, CM, CP, S, R, TH_S, TH_T, MB)                                                            \
+    if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0))                          \
+        return pt ? launch_conv_tc<CI, CM, CP, S, R, TH_T, true, MB>(in, out, w1, b1, w2, b2, n, H, W, st)   \
+                  : launch_conv_tc<CI, CM, CP, S, R, TH_S, false, MB>(in, out, w1, b1, w2, b2, n, H, W, st);
+        CTCASE(32, 16, 0, 1, false, 15, 15, 2)     // blocks.0.0  ConvBnAct: two CTAs per SM
+        CTCASE(16, 64, 32, 2, false, 15, 15, 1)    // blocks.1.0  EdgeResidual s2
+        CTCASE(32, 128, 32, 1, true, 15, 15, 1)    // blocks.1.1
+        CTCASE(32, 128, 48, 2, false, 3, 7, 1)     // blocks.2.0  (P in shared memory only fits with 3-row tiles)
+#undef CTCASE
+    }
     if (cin == 32 && cmid == 128 && stride == 1 && cproj == 32 && res == 1)     // blocks.1.1: tcgen05 implicit GEMM
         return launch_conv3_tc<32, 128, 32>(in, out, w1, b1, w2, b2, n, H, W, st);
 #define C3CASE(CI, CM, S, CP, R, MB, MT) \

@@ -69,7 +69,10 @@ def test_stem(lib, dtype, hflip):
 @pytest.mark.parametrize("cin,cmid,stride,cproj,res", [(32, 16, 1, 0, 0), (16, 64, 2, 32, 0), (32, 128, 1, 32, 1),
                                                        (32, 128, 2, 48, 0), (48, 192, 1, 48, 1)])
 @pytest.mark.parametrize("hw", [(24, 40), (46, 34)])
-def test_conv3x3(lib, cin, cmid, stride, cproj, res, hw):
+@pytest.mark.parametrize("mode", [2, 1, 0])
+def test_conv3x3(lib, cin, cmid, stride, cproj, res, hw, mode):
+    """mode = mds_set_conv_mode: 2 = conv_tc_kernel with the expanded tensor in tensor memory (default), 1 = staged in shared
+    memory, 0 = the round-1 kernels.  blocks.2.1 (48, 192) runs the same kernel in every mode."""
     n, (H, W) = 2, hw
     x = h16(torch.randn(n, cin, H, W, generator=gen(1)))
     w1 = h16(torch.randn(cmid, cin, 3, 3, generator=gen(2)) * (2.0 / (9 * cin)) ** 0.5)
@@ -94,11 +97,56 @@ def test_conv3x3(lib, cin, cmid, stride, cproj, res, hw):
     d_w2 = w2.contiguous().to(DEV) if cproj else None
     d_b2 = b2.to(DEV) if cproj else None
     out = torch.zeros((n, Ho, Wo, cout), dtype=torch.float16, device=DEV)
-    ok(lib.mds_k_conv3x3(d_x.data_ptr(), out.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(),
-                         d_w2.data_ptr() if cproj else None, d_b2.data_ptr() if cproj else None,
-                         n, H, W, cin, cmid, stride, cproj, res, None), lib)
-    torch.cuda.synchronize()
+    ok(lib.mds_set_conv_mode(mode), lib)
+    try:
+        ok(lib.mds_k_conv3x3(d_x.data_ptr(), out.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(),
+                             d_w2.data_ptr() if cproj else None, d_b2.data_ptr() if cproj else None,
+                             n, H, W, cin, cmid, stride, cproj, res, None), lib)
+        torch.cuda.synchronize()
+    finally:
+        lib.mds_set_conv_mode(2)
     assert rel(nchw(out), ref) <= TOL
+
+
+@pytest.mark.parametrize("cin,cmid,stride,cproj,res,hw", [(32, 16, 1, 0, 0, (368, 640)), (16, 64, 2, 32, 0, (368, 640)),
+                                                          (32, 128, 2, 48, 0, (184, 320))])
+@pytest.mark.parametrize("mode", [2, 1])
+def test_conv_tc_many_tiles(lib, cin, cmid, stride, cproj, res, hw, mode):
+    """blocks.0.0 / 1.0 / 2.0 at their real resolutions, 3 images: every persistent CTA loops over several halo tiles, so both
+    tile buffers and both accumulators wrap their mbarrier phases; a second launch must reproduce the first bit for bit."""
+    n, (H, W) = 3, hw
+    x = h16(torch.randn(n, cin, H, W, generator=gen(1)))
+    w1 = h16(torch.randn(cmid, cin, 3, 3, generator=gen(2)) * (2.0 / (9 * cin)) ** 0.5)
+    b1 = torch.randn(cmid, generator=gen(3)) * 0.1
+    xf = x.float()
+    y = F.conv2d(xf, w1.float(), b1, padding=1) if stride == 1 else F.conv2d(F.pad(xf, (0, 1, 0, 1)), w1.float(), b1, stride=2)
+    y = F.silu(y)
+    w2 = b2 = None
+    if cproj:
+        w2 = h16(torch.randn(cproj, cmid, generator=gen(4)) * (1.0 / cmid) ** 0.5)
+        b2 = torch.randn(cproj, generator=gen(5)) * 0.1
+        y = F.conv2d(h16(y).float(), w2.float()[:, :, None, None], b2)
+    cout = cproj or cmid
+    Ho, Wo = y.shape[-2:]
+    d_x = nhwc(x).to(DEV)
+    d_w1 = w1.permute(0, 2, 3, 1).reshape(cmid, -1).contiguous().to(DEV)
+    d_b1 = b1.to(DEV)
+    d_w2 = w2.contiguous().to(DEV) if cproj else None
+    d_b2 = b2.to(DEV) if cproj else None
+    outs = []
+    ok(lib.mds_set_conv_mode(mode), lib)
+    try:
+        for _ in range(2):
+            out = torch.full((n, Ho, Wo, cout), float("nan"), dtype=torch.float16, device=DEV)
+            ok(lib.mds_k_conv3x3(d_x.data_ptr(), out.data_ptr(), d_w1.data_ptr(), d_b1.data_ptr(),
+                                 d_w2.data_ptr() if cproj else None, d_b2.data_ptr() if cproj else None,
+                                 n, H, W, cin, cmid, stride, cproj, res, None), lib)
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        lib.mds_set_conv_mode(2)
+    assert rel(nchw(outs[0]), y) <= TOL
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_conv3x3_tcgen05_many_tiles(lib):

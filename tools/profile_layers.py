@@ -18,12 +18,14 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--chunk-images", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--tail-mode", type=int, default=3)
+ap.add_argument("--conv-mode", type=int, default=2)
 a = ap.parse_args()
 H, W, SH, T = 736, 1280, 720, 5
 dev = torch.device("cuda:0")
 net = MultiDimStacker("tf_efficientnetv2_b0.in1k", 2, num_3d_blocks=4, expansion_3d_ratio=3, chunk_images=a.chunk_images).init_random_(1).to(dev).eval()
 eng = net.engine(dev)
 eng.lib.mds_set_tail_mode(a.tail_mode)
+eng.lib.mds_set_conv_mode(a.conv_mode)
 x = torch.randint(0, 256, (a.batch, 15, SH, W), dtype=torch.uint8, device=dev)
 desc = eng.frames_desc(x, H, W, 3 * SH * W, SH * W)
 for _ in range(2):
