@@ -16,8 +16,9 @@
 //   warp 0 / lane 0 : TMA producer (double-buffered halo tiles)
 //   warp 1 / lane 0 : MMA issuer: per 128-pixel M tile 9 x CIN/16 tcgen05.mma (N = CMID) + one against a "ones" tile that
 //                     adds the bias; later CMID/16 MMAs (N = CPROJ) for the projection
-//   other warps     : epilogue, two ping-pong groups: TMEM -> SiLU -> fp16 -> TMEM / smem (A operand of the projection);
-//                     then TMEM -> + residual -> fp16 -> 32-byte global stores
+//   other warps     : epilogue (4 TMEM lane quadrants x up to 4 column parts): E1 = TMEM -> SiLU -> fp16 -> TMEM / smem
+//                     (A operand of the projection), E2 = TMEM -> + residual -> fp16 -> 32-byte global stores.  Every warp
+//                     streams 8-column chunks with the next tcgen05.ld in flight, E2 of M tile t-1 comes after E1 of tile t
 #pragma once
 #include <cuda.h>
 
@@ -54,8 +55,10 @@ struct ConvTcCfg {
     static constexpr int MAX_OFF = STRIDE == 1 ? 2 * PW + 2 : PW + 1;
     static constexpr int OVER = MT_MAX * 128 + MAX_OFF > PIX ? MT_MAX * 128 + MAX_OFF - PIX : 0;   // pixels the last M tile over-reads
     static constexpr int TILE_ALLOC = ((TILE_BYTES + OVER * 16 + 127) / 128) * 128;
-    static constexpr int HALVES = CMID >= 32 ? 2 : 1;            // epilogue warps that share a TMEM lane quadrant and accumulator
-    static constexpr int EPI_WARPS = 8 * HALVES;
+    static constexpr int PARTS = CMID >= 64 ? 4 : CMID / 16;     // epilogue warps that share a TMEM lane quadrant (column parts)
+    static constexpr int GROUPS = CPROJ > 0 ? 1 : 2;             // epilogue groups; group e takes the M tiles t with t % GROUPS == e
+    static constexpr int ND1 = CPROJ > 0 ? 2 : 4;                // conv accumulators in flight
+    static constexpr int EPI_WARPS = 4 * PARTS * GROUPS;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int W1_BYTES = 9 * CIN * CMID * 2;          // [tap][c8][n][8]
     static constexpr int W2_BYTES = CMID * CPROJ * 2;            // [c8][n][8]
@@ -63,9 +66,9 @@ struct ConvTcCfg {
     static constexpr int ONES_BYTES = 2 * 128 * 16;              // [2 planes][128 rows][8]: (row, k=0,1) = 1
     static constexpr int BM1_BYTES = 2 * CMID * 16;              // [2 planes][CMID][8]: (n, k=0,1) = bias hi/lo
     static constexpr int BM2_BYTES = 2 * CPROJ * 16;
-    // tensor memory columns: D1[2] | P[2] (packed fp16, PT only) | D2[2]
+    // tensor memory columns: D1[ND1] | P[2] (packed fp16, PT only) | D2[2]
     static constexpr int D1_STRIDE = CMID < 32 ? 32 : CMID;
-    static constexpr int P_COL = 2 * D1_STRIDE;
+    static constexpr int P_COL = ND1 * D1_STRIDE;
     static constexpr int D2_COL = P_COL + (CPROJ > 0 ? CMID : 0);
     static constexpr int D2_STRIDE = 64;
     static constexpr int TMEM_USED = D2_COL + (CPROJ > 0 ? 2 * D2_STRIDE : 0);
@@ -77,6 +80,8 @@ struct ConvTcCfg {
     static_assert(PHASE_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
     static_assert(TMEM_USED <= 512, "TMEM columns");
     static_assert(CPROJ <= 64, "projection accumulator stride");
+    static_assert(CPROJ == 0 || CPROJ / 16 <= PARTS, "one projection column group per epilogue part");
+    static_assert((CMID / 16) % PARTS == 0, "column groups split evenly over the parts");
     static_assert(SMEM <= 232448, "shared memory");
 };
 
@@ -91,6 +96,12 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
                  : "memory");
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -115,12 +126,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, ConvTcParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bm2 + Cfg::BM2_BYTES);
     uint64_t* tile_full = bars;          // [2]
     uint64_t* tile_empty = bars + 2;     // [2]
-    uint64_t* d1_full = bars + 4;        // [2]
-    uint64_t* d1_empty = bars + 6;       // [2]
-    uint64_t* p_full = bars + 8;         // [2]
-    uint64_t* d2_full = bars + 10;       // [2]
-    uint64_t* d2_empty = bars + 12;      // [2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* d1_full = bars + 4;        // [ND1 <= 4]
+    uint64_t* d1_empty = bars + 8;       // [ND1 <= 4]
+    uint64_t* p_full = bars + 12;        // [2]
+    uint64_t* d2_full = bars + 14;       // [2]
+    uint64_t* d2_empty = bars + 16;      // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -129,10 +140,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, ConvTcParams p) {
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tile_full[i], 1); mbar_init(&tile_empty[i], 1);
-            mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], Cfg::EPI_WARPS / 2);
-            mbar_init(&p_full[i], Cfg::EPI_WARPS / 2);
-            mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], Cfg::EPI_WARPS / 2);
+            mbar_init(&p_full[i], Cfg::EPI_WARPS);
+            mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], Cfg::EPI_WARPS);
         }
+        for (int i = 0; i < Cfg::ND1; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], Cfg::EPI_WARPS / Cfg::GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < Cfg::NPH; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
@@ -189,28 +200,34 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, ConvTcParams p) {
     };
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (whole warp converged, one elected lane issues) =================
+        {
             int i = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
                 int n, y0, x0, nm;
                 tile_geom(tile, n, y0, x0, nm);
                 const int buf = i & 1;
                 mbar_wait(&tile_empty[buf], (((uint32_t)i >> 1) & 1) ^ 1);
-                mbar_expect_tx(&tile_full[buf], (uint32_t)Cfg::TILE_BYTES);
-                unsigned char* dst = s_tile + (size_t)buf * Cfg::TILE_ALLOC;
-                if constexpr (STRIDE == 1) {
-                    tma_load_5d(dst, &maps.m[0], &tile_full[buf], 0, x0 - 1, y0 - 1, 0, n);
-                } else {
+                if (elect_one()) {
+                    mbar_expect_tx(&tile_full[buf], (uint32_t)Cfg::TILE_BYTES);
+                    unsigned char* dst = s_tile + (size_t)buf * Cfg::TILE_ALLOC;
+                    if constexpr (STRIDE == 1) {
+                        tma_load_5d(dst, &maps.m[0], &tile_full[buf], 0, x0 - 1, y0 - 1, 0, n);
+                    } else {
 #pragma unroll
-                    for (int ph = 0; ph < 4; ++ph)
-                        tma_load_5d(dst + (size_t)ph * Cfg::PHASE_BYTES, &maps.m[ph], &tile_full[buf], 0, x0, y0, 0, n);
+                        for (int ph = 0; ph < 4; ++ph)
+                            tma_load_5d(dst + (size_t)ph * Cfg::PHASE_BYTES, &maps.m[ph], &tile_full[buf], 0, x0, y0, 0, n);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The WHOLE warp runs the control flow (waits, loops) converged and one elected lane issues: a tcgen05.mma under
+        // `if (lane == 0)` makes ptxas wrap every UTCHMMA in an election loop (ELECT / BRA.U.ANY), measured at 62-94 clocks per
+        // MMA whatever its shape; under elect.sync it is a single predicated instruction (tools/mma_probe.cu: 39 clocks at N = 16).
+        {
             const uint32_t idesc1 = tc_idesc(128, CMID);
             const uint32_t w1a = smem_u32(s_w1), onesa = smem_u32(s_ones);
             const uint64_t ones_desc = tc_desc_nosw(onesa, 128 * 16);
@@ -226,17 +243,20 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, ConvTcParams p) {
                     mbar_wait(&d2_empty[a], ph ^ 1);
                     tc_fence_after();
                     const uint32_t d2 = tmem_base + Cfg::D2_COL + a * Cfg::D2_STRIDE;
-                    tc_mma_f16(d2, ones_desc, bm2_desc, idesc2, 0);
+                    if (elect_one()) {
+                        tc_mma_f16(d2, ones_desc, bm2_desc, idesc2, 0);
 #pragma unroll
-                    for (int kk = 0; kk < CMID / 16; ++kk) {
-                        const uint64_t bdesc = tc_desc_nosw(w2a + kk * 2 * (CPROJ * 16), CPROJ * 16);
-                        if constexpr (PT) {
-                            tc_mma_f16_ts(d2, tmem_base + Cfg::P_COL + a * (CMID / 2) + kk * 8, bdesc, idesc2, 1);
-                        } else {
-                            tc_mma_f16(d2, tc_desc_nosw(smem_u32(s_p) + a * Cfg::P_BYTES + kk * 2 * (128 * 16), 128 * 16), bdesc, idesc2, 1);
+                        for (int kk = 0; kk < CMID / 16; ++kk) {
+                            const uint64_t bdesc = tc_desc_nosw(w2a + kk * 2 * (CPROJ * 16), CPROJ * 16);
+                            if constexpr (PT) {
+                                tc_mma_f16_ts(d2, tmem_base + Cfg::P_COL + a * (CMID / 2) + kk * 8, bdesc, idesc2, 1);
+                            } else {
+                                tc_mma_f16(d2, tc_desc_nosw(smem_u32(s_p) + a * Cfg::P_BYTES + kk * 2 * (128 * 16), 128 * 16), bdesc, idesc2, 1);
+                            }
                         }
+                        tc_commit(&d2_full[a]);
                     }
-                    tc_commit(&d2_full[a]);
+                    __syncwarp();
                 }
             };
             int i = 0, t = 0;
@@ -248,140 +268,166 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, ConvTcParams p) {
                 tc_fence_after();
                 const uint32_t ta = smem_u32(s_tile + (size_t)buf * Cfg::TILE_ALLOC);
                 for (int m = 0; m < nm; ++m, ++t) {
-                    const int a = t & 1;
-                    mbar_wait(&d1_empty[a], (((uint32_t)t >> 1) & 1) ^ 1);
+                    const int a = t % Cfg::ND1;
+                    mbar_wait(&d1_empty[a], (((uint32_t)t / Cfg::ND1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d1 = tmem_base + a * Cfg::D1_STRIDE;
-                    tc_mma_f16(d1, ones_desc, bm1_desc, idesc1, 0);                     // D1 = bias
+                    if (elect_one()) {
+                        tc_mma_f16(d1, ones_desc, bm1_desc, idesc1, 0);                     // D1 = bias
 #pragma unroll
-                    for (int rs = 0; rs < 9; ++rs) {
-                        const int r = rs / 3, s = rs - r * 3;
-                        const int phase = STRIDE == 1 ? 0 : (r & 1) * 2 + (s & 1);
-                        const int off = STRIDE == 1 ? r * Cfg::PW + s : (r >> 1) * Cfg::PW + (s >> 1);
-                        const uint32_t a_addr = ta + (uint32_t)(phase * Cfg::PHASE_BYTES) + (uint32_t)(m * 128 + off) * 16u;
+                        for (int rs = 0; rs < 9; ++rs) {
+                            const int r = rs / 3, s = rs - r * 3;
+                            const int phase = STRIDE == 1 ? 0 : (r & 1) * 2 + (s & 1);
+                            const int off = STRIDE == 1 ? r * Cfg::PW + s : (r >> 1) * Cfg::PW + (s >> 1);
+                            const uint32_t a_addr = ta + (uint32_t)(phase * Cfg::PHASE_BYTES) + (uint32_t)(m * 128 + off) * 16u;
 #pragma unroll
-                        for (int kc = 0; kc < CIN / 16; ++kc)
-                            tc_mma_f16(d1, tc_desc_nosw(a_addr + kc * 2 * Cfg::PLANE, Cfg::PLANE),
-                                       tc_desc_nosw(w1a + (rs * (CIN / 8) + kc * 2) * (CMID * 16), CMID * 16), idesc1, 1);
+                            for (int kc = 0; kc < CIN / 16; ++kc)
+                                tc_mma_f16(d1, tc_desc_nosw(a_addr + kc * 2 * Cfg::PLANE, Cfg::PLANE),
+                                           tc_desc_nosw(w1a + (rs * (CIN / 8) + kc * 2) * (CMID * 16), CMID * 16), idesc1, 1);
+                        }
+                        tc_commit(&d1_full[a]);
                     }
-                    tc_commit(&d1_full[a]);
+                    __syncwarp();
                     if (t >= 1) mma2(t - 1);
                 }
-                tc_commit(&tile_empty[buf]);            // every MMA that reads this halo tile has been issued
+                if (elect_one()) tc_commit(&tile_empty[buf]);            // every MMA that reads this halo tile has been issued
+                __syncwarp();
             }
             if (t >= 1) mma2(t - 1);
         }
     } else {
-        // ================= epilogue: two groups of 4 * HALVES warps =================
+        // ================= epilogue: GROUPS x 4 lane quadrants x PARTS column parts =================
+        // Each warp streams its columns of an M tile in 8-column chunks: the tcgen05.ld of chunk c+1 (and, across M tiles, of
+        // chunk 0 of the next tile) is in flight while chunk c goes through SiLU, so the TMEM read port (64 B / clk), the SFU
+        // pipe and the tensor core overlap.  E2 (projection accumulator -> + residual -> global) of M tile t-1 is issued after
+        // E1 of tile t: its MMA ran on the tensor core meanwhile.
         const int q = warp & 3;                         // TMEM lane quadrant
-        const int e = ((warp - 2) >> 2) & 1;            // group = accumulator index
-        const int half = (warp - 2) >> 3;               // which part of the columns (0 when HALVES == 1)
+        const int ew = (warp - 2) >> 2;                 // 0 .. GROUPS * PARTS - 1
+        const int grp = ew / Cfg::PARTS, part = ew - grp * Cfg::PARTS;
         const int row = q * 32 + lane;                  // row of the M tile = linear tile pixel
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-        int i = 0, t = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
-            int n, y0, x0, nm;
-            tile_geom(tile, n, y0, x0, nm);
-            for (int m = 0; m < nm; ++m, ++t) {
-                if ((t & 1) != e) continue;
-                const uint32_t ph = ((uint32_t)t >> 1) & 1;
-                const int lp = m * 128 + row;                                    // linear pixel inside the row-major tile
-                const int ry = lp / Cfg::PW, cx = lp - ry * Cfg::PW;
-                const int oy = y0 + ry, ox = x0 + cx;
-                const bool ok = (cx < Cfg::TW) && (ry < Cfg::TH) && (oy < p.Ho) && (ox < p.Wo);
-                const size_t pix = ((size_t)n * p.Ho + (ok ? oy : 0)) * p.Wo + (ok ? ox : 0);
-
-                // ---- epilogue 1: D1 -> SiLU -> fp16 -> P (A operand of the projection) or, without projection, global ----
-                mbar_wait(&d1_full[e], ph);
+        constexpr int NG2 = CPROJ / 16;                 // 16-column groups of the projection: part g takes group g
+        constexpr int CW = 8;                           // columns per chunk
+        constexpr int COLS = CMID / Cfg::PARTS;         // columns per warp
+        constexpr int NCH = COLS / CW;                  // chunks per warp and M tile (even)
+        static_assert(NCH % 2 == 0, "chunks are consumed in pairs (16 channels = one 32-byte store)");
+        uint32_t rv[8], rv_next[8];      // residual of the M tile in E2 / of the tile in E1 (requested a whole E1 phase ahead)
+        auto epi2 = [&](int u, bool okp, size_t pixp) {
+            if constexpr (PROJ) {
+                const int a = u & 1;
+                mbar_wait(&d2_full[a], ((uint32_t)u >> 1) & 1);
                 tc_fence_after();
-                constexpr int G1 = CMID / 16 / Cfg::HALVES;      // 16-column groups per warp
-                constexpr int GC = G1 >= 2 ? 2 : 1;              // groups in flight
+                uint32_t v2[16];
+                if (part < NG2) tc_ld16(t_row + (uint32_t)(Cfg::D2_COL + a * Cfg::D2_STRIDE + part * 16), v2);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d2_empty[a]);
+                if (okp && part < NG2) {
+                    uint32_t pk[8];
 #pragma unroll
-                for (int g0 = 0; g0 < G1; g0 += GC) {
-                    uint32_t v[GC][16];
-#pragma unroll
-                    for (int j = 0; j < GC; ++j) tc_ld16(t_row + (uint32_t)(e * Cfg::D1_STRIDE + (half * G1 + g0 + j) * 16), v[j]);
-                    tc_wait_ld();
-                    if (g0 + GC >= G1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&d1_empty[e]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < GC; ++j) {
-                        const int g = half * G1 + g0 + j;       // columns [16g, 16g+16) = channels = planes 2g, 2g+1
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int h = 0; h < 8; ++h)
-                            pk[h] = pack_half2(silu_f(__uint_as_float(v[j][2 * h])), silu_f(__uint_as_float(v[j][2 * h + 1])));
-                        if constexpr (!PROJ) {
-                            if (ok) st_global_v8(p.out + pix * COUT + g * 16, pk);
-                        } else if constexpr (PT) {
-                            tc_st8(t_row + (uint32_t)(Cfg::P_COL + e * (CMID / 2) + g * 8), pk);
-                        } else {
-                            unsigned char* pbuf = s_p + e * Cfg::P_BYTES;
-                            *reinterpret_cast<uint4*>(pbuf + (size_t)(2 * g) * (128 * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            *reinterpret_cast<uint4*>(pbuf + (size_t)(2 * g + 1) * (128 * 16) + row * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    for (int h = 0; h < 8; ++h) {
+                        float x0f = __uint_as_float(v2[2 * h]), x1f = __uint_as_float(v2[2 * h + 1]);
+                        if constexpr (RES) {
+                            const float2 r2 = unpack_half2(rv[h]);
+                            x0f += r2.x; x1f += r2.y;
                         }
+                        pk[h] = pack_half2(x0f, x1f);
                     }
-                }
-                if constexpr (PROJ) {
-                    if constexpr (PT) {
-                        tc_wait_st();
-                        tc_fence_before();
-                    } else {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // P written by the generic proxy, read by tcgen05.mma
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&p_full[e]);
-
-                    // ---- epilogue 2: D2 (+ residual) -> fp16 -> global ----
-                    constexpr int NG2 = CPROJ / 16;          // 16-column groups: 2 (CPROJ 32) or 3 (CPROJ 48)
-                    // half 0 takes groups 0 and 2, half 1 takes group 1
-                    uint32_t rv[2][8];
-                    if constexpr (RES) {
-                        if (ok) {
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const int g = half + 2 * j;
-                                if (g < NG2) ld_global_v8(p.in + pix * CIN + g * 16, rv[j]);
-                            }
-                        }
-                    }
-                    mbar_wait(&d2_full[e], ph);
-                    tc_fence_after();
-                    uint32_t v2[2][16];
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int g = half + 2 * j;
-                        if (g < NG2) tc_ld16(t_row + (uint32_t)(Cfg::D2_COL + e * Cfg::D2_STRIDE + g * 16), v2[j]);
-                    }
-                    tc_wait_ld();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&d2_empty[e]);
-                    if (ok) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int g = half + 2 * j;
-                            if (g < NG2) {
-                                uint32_t pk[8];
-#pragma unroll
-                                for (int h = 0; h < 8; ++h) {
-                                    float x0f = __uint_as_float(v2[j][2 * h]), x1f = __uint_as_float(v2[j][2 * h + 1]);
-                                    if constexpr (RES) {
-                                        const float2 r2 = unpack_half2(rv[j][h]);
-                                        x0f += r2.x; x1f += r2.y;
-                                    }
-                                    pk[h] = pack_half2(x0f, x1f);
-                                }
-                                st_global_v8(p.out + pix * COUT + g * 16, pk);
-                            }
-                        }
-                    }
+                    st_global_v8(p.out + pixp * COUT + part * 16, pk);
                 }
             }
+        };
+        // iterate over the M tiles (tile, m) of this CTA; T = running index over all of them, this group owns T % GROUPS == grp
+        int tile = blockIdx.x, m = 0, T = 0, n = 0, y0 = 0, x0 = 0, nm = 0;
+        bool have = tile < ntiles;
+        if (have) tile_geom(tile, n, y0, x0, nm);
+        auto step = [&]() {          // advance (tile, m, T) to the next M tile of the CTA
+            ++T;
+            if (++m == nm) {
+                tile += gridDim.x; m = 0;
+                have = tile < ntiles;
+                if (have) tile_geom(tile, n, y0, x0, nm);
+            }
+        };
+        while (have && T % Cfg::GROUPS != grp) step();
+        uint32_t buf[2][CW];
+        auto ld_first = [&]() {      // wait for the accumulator of M tile T and request its first chunk
+            const int a = T % Cfg::ND1;
+            mbar_wait(&d1_full[a], ((uint32_t)T / Cfg::ND1) & 1);
+            tc_fence_after();
+            tc_ld8(t_row + (uint32_t)(a * Cfg::D1_STRIDE + part * COLS), buf[0]);
+        };
+        if (have) { ld_first(); tc_wait_ld(); }
+        int u_prev = -1;
+        bool ok_prev = false;
+        size_t pix_prev = 0;
+        while (have) {
+            const int a = T % Cfg::ND1;
+            const int lp = m * 128 + row;                                    // linear pixel inside the row-major tile
+            const int ry = lp / Cfg::PW, cx = lp - ry * Cfg::PW;
+            const int oy = y0 + ry, ox = x0 + cx;
+            const bool ok = (cx < Cfg::TW) && (ry < Cfg::TH) && (oy < p.Ho) && (ox < p.Wo);
+            const size_t pix = ((size_t)n * p.Ho + (ok ? oy : 0)) * p.Wo + (ok ? ox : 0);
+            const int u_cur = T;
+
+            if constexpr (RES) {
+                if (ok && part < NG2) ld_global_v8(p.in + pix * CIN + part * 16, rv_next);
+            }
+            // ---- E1: D1 -> SiLU -> fp16 -> P (A operand of the projection) or, without projection, global ----
+            uint32_t pk[8];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (c + 1 < NCH) tc_ld8(t_row + (uint32_t)(a * Cfg::D1_STRIDE + part * COLS + (c + 1) * CW), buf[(c + 1) & 1]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float x4[4] = {__uint_as_float(buf[c & 1][4 * h]), __uint_as_float(buf[c & 1][4 * h + 1]),
+                                   __uint_as_float(buf[c & 1][4 * h + 2]), __uint_as_float(buf[c & 1][4 * h + 3])};
+                    silu4(x4);
+                    pk[(c & 1) * 4 + 2 * h] = pack_half2(x4[0], x4[1]);
+                    pk[(c & 1) * 4 + 2 * h + 1] = pack_half2(x4[2], x4[3]);
+                }
+                if (c & 1) {                                 // 16 channels ready: columns [col, col + 16)
+                    const int col = part * COLS + (c - 1) * CW;
+                    if constexpr (!PROJ) {
+                        if (ok) st_global_v8(p.out + pix * COUT + col, pk);
+                    } else if constexpr (PT) {
+                        tc_st8(t_row + (uint32_t)(Cfg::P_COL + a * (CMID / 2) + col / 2), pk);
+                    } else {
+                        unsigned char* pbuf = s_p + a * Cfg::P_BYTES;
+                        *reinterpret_cast<uint4*>(pbuf + (size_t)(col / 8) * (128 * 16) + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(pbuf + (size_t)(col / 8 + 1) * (128 * 16) + row * 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+                if (c + 1 < NCH) tc_wait_ld();
+                if (c + 2 == NCH) {                          // the last chunk of this accumulator is in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d1_empty[a]);
+                }
+            }
+            if constexpr (PROJ) {
+                if constexpr (PT) {
+                    tc_wait_st();
+                    tc_fence_before();
+                } else {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // P written by the generic proxy, read by tcgen05.mma
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[a]);
+            }
+            // ---- next M tile of this group: request its first chunk, then E2 of the previous one while it is in flight ----
+            do step(); while (have && T % Cfg::GROUPS != grp);
+            if (have) ld_first();
+            if (PROJ && u_prev >= 0) epi2(u_prev, ok_prev, pix_prev);       // ends with a tcgen05.wait::ld
+            else tc_wait_ld();
+            u_prev = u_cur; ok_prev = ok; pix_prev = pix;
+            if constexpr (RES) {
+#pragma unroll
+                for (int h = 0; h < 8; ++h) rv[h] = rv_next[h];
+            }
         }
+        if (PROJ && u_prev >= 0) epi2(u_prev, ok_prev, pix_prev);
     }
 
     tc_fence_before();
