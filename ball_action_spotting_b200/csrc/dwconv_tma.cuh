@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
     __syncthreads();
     pdl_wait();       // weights above are constants; the input rows below come from the previous kernel
 
-    auto issue = [&](int js) {      // thread 0: stage use js -> ring slot js % NST
+    auto issue = [&](int js) {      // elected lane of warp 0: stage use js -> ring slot js % NST
         const int st = js % Cfg::NST;
         mbar_wait(&empty[st], ((js / Cfg::NST) & 1) ^ 1);
         mbar_expect_tx(&full[st], (uint32_t)Cfg::STAGEB);
@@ -156,10 +156,13 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
         else
             dt_tma_4d(s_ring + (size_t)st * Cfg::STAGEB, &tmIn, &full[st], c_slab, xi0, yi0 + js * Cfg::RPS, n);
     };
-    if (tid == 0) {
+    if (warp == 0) {              // one elected lane of the converged warp issues (no ptxas election loop around UTMALDG)
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < Cfg::NST - 1; ++j)
-            if (j < nstg) issue(j);
+            for (int j = 0; j < Cfg::NST - 1; ++j)
+                if (j < nstg) issue(j);
+        }
+        __syncwarp();
     }
 
     float2 lsum = make_float2(0.f, 0.f);
@@ -211,7 +214,10 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
 
     int k = 0;
     for (int js = 0; js < nstg; ++js) {
-        if (tid == 0 && js + Cfg::NST - 1 < nstg) issue(js + Cfg::NST - 1);
+        if (warp == 0 && js + Cfg::NST - 1 < nstg) {
+            if (elect_one()) issue(js + Cfg::NST - 1);
+            __syncwarp();
+        }
         const int st = js % Cfg::NST;
         mbar_wait(&full[st], (js / Cfg::NST) & 1);
         const uint32_t sbase = lds_lane + (uint32_t)st * Cfg::STAGEB;

@@ -197,7 +197,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        // The whole warp runs the loops converged and one elected lane (elect.sync) issues: under `if (lane == 0)` ptxas wraps
+        // every warp-uniform instruction (UTMALDG, UTCHMMA, UTCBAR) in an election loop, 60-90 clocks each (tools/mma_probe.cu).
+        {
             int stage = 0;
             uint32_t phase = 0;
             if (p.streamed) {
@@ -207,15 +209,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kb = 0; kb <= num_kb; ++kb) {              // block num_kb = the bias block
                         mbar_wait(&b_empty[stage], phase ^ 1);
                         unsigned char* st = s_ring + (size_t)stage * stage_bytes;
-                        if (kb < num_kb) {
-                            mbar_expect_tx(&b_full[stage], (uint32_t)(kTcABytes + b_bytes));
-                            tma_load_2d(st, &tmA, &b_full[stage], kb * kTcBK, row0);
-                            if (gated) tma_load_2d(st + b_off, &tmB, &b_full[stage], kb * kTcBK, 0);
-                            else tma_load_3d(st + b_off, &tmB, &b_full[stage], kb * kTcBK, 0, img);
-                        } else {
-                            mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
-                            tma_load_2d(st + b_off, &tmBias, &b_full[stage], 0, 0);
+                        if (elect_one()) {
+                            if (kb < num_kb) {
+                                mbar_expect_tx(&b_full[stage], (uint32_t)(kTcABytes + b_bytes));
+                                tma_load_2d(st, &tmA, &b_full[stage], kb * kTcBK, row0);
+                                if (gated) tma_load_2d(st + b_off, &tmB, &b_full[stage], kb * kTcBK, 0);
+                                else tma_load_3d(st + b_off, &tmB, &b_full[stage], kb * kTcBK, 0, img);
+                            } else {
+                                mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
+                                tma_load_2d(st + b_off, &tmBias, &b_full[stage], 0, 0);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -223,9 +228,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 auto load_a = [&](int i, int mt) {      // A row tile i of this CTA -> buffer i & 1
                     const int ab = i & 1;
                     mbar_wait(&a_empty[ab], (((uint32_t)i >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&a_full[ab], (uint32_t)(num_kb * kTcABytes));
-                    for (int kb = 0; kb < num_kb; ++kb)
-                        tma_load_2d(s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes, &tmA, &a_full[ab], kb * kTcBK, mt * kTcBM);
+                    if (elect_one()) {
+                        mbar_expect_tx(&a_full[ab], (uint32_t)(num_kb * kTcABytes));
+                        for (int kb = 0; kb < num_kb; ++kb)
+                            tma_load_2d(s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes, &tmA, &a_full[ab], kb * kTcBK, mt * kTcBM);
+                    }
+                    __syncwarp();
                 };
                 int i = 0;
                 if ((int)blockIdx.x < p.m_tiles) load_a(0, blockIdx.x);
@@ -235,17 +243,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int nt = 0; nt < p.n_tiles; ++nt)
                         for (int kb = 0; kb <= num_kb; ++kb) {              // block num_kb = the bias block
                             mbar_wait(&b_empty[stage], phase ^ 1);
-                            mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
-                            if (kb < num_kb) tma_load_2d(s_ring + (size_t)stage * stage_bytes, &tmB, &b_full[stage], kb * kTcBK, nt * p.BN);
-                            else tma_load_2d(s_ring + (size_t)stage * stage_bytes, &tmBias, &b_full[stage], 0, nt * p.BN);
+                            if (elect_one()) {
+                                mbar_expect_tx(&b_full[stage], (uint32_t)b_bytes);
+                                if (kb < num_kb) tma_load_2d(s_ring + (size_t)stage * stage_bytes, &tmB, &b_full[stage], kb * kTcBK, nt * p.BN);
+                                else tma_load_2d(s_ring + (size_t)stage * stage_bytes, &tmBias, &b_full[stage], 0, nt * p.BN);
+                            }
+                            __syncwarp();
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+        {
             const uint32_t idesc = tc_idesc(kTcBM, p.BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -266,15 +277,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const unsigned char* a_src = bias_blk ? s_ones : (p.streamed ? st : s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes);
                         const uint64_t adesc = tc_smem_desc(smem_u32(a_src));
                         const uint64_t bdesc = tc_smem_desc(smem_u32(st + b_off));
-                        const int nk = bias_blk ? 1 : kTcBK / 16;       // the bias block only has K = 16 worth of data
-                        for (int k = 0; k < nk; ++k)     // advance 16 K-elements = 32 B inside the swizzle atom (>>4 = 2)
-                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                        tc_commit(&b_empty[stage]);                  // stage reusable once these MMAs have read it
+                        if (elect_one()) {
+                            if (bias_blk) {                  // the bias block only has K = 16 worth of data
+                                tc_mma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < kTcBK / 16; ++k)     // advance 16 K-elements = 32 B inside the swizzle atom (>>4 = 2)
+                                    tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                            }
+                            tc_commit(&b_empty[stage]);                  // stage reusable once these MMAs have read it
+                            if (bias_blk) tc_commit(&acc_full[acc]);     // accumulator complete
+                        }
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(&acc_full[acc]);                       // accumulator complete
                 }
-                if (!p.streamed) tc_commit(&a_empty[ab]);            // every MMA that reads this A tile has been issued
+                if (!p.streamed) {
+                    if (elect_one()) tc_commit(&a_empty[ab]);            // every MMA that reads this A tile has been issued
+                    __syncwarp();
+                }
             }
         }
     } else if (gated && warp >= 2 + kTcEpiWarps / 2) {
