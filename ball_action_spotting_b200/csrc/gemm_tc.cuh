@@ -33,14 +33,20 @@ struct TcGemmParams {
     int tmem_cols;        // power of two >= 2*BN
     int streamed;         // 0: A row tile resident in smem, swept over all N tiles (K <= 192)
                           // 1: A streamed with B through the ring (any K), one N tile
+    long long* trace;     // -DMDS_GEMM_TRACE builds only: clock64 stamps of CTA 0 (tools/conv_trace.sh)
     const float* gate;    // streamed mode: nullptr -> B = per-image pre-gated weights (3-D map);
                           // else [n_img][K] fp32 SE gates: B = the shared weights (2-D map) and warps 10-17 multiply every A
                           // block by the image's gate in shared memory (fp32 product, one rounding) before the MMAs read it
 };
 
+#ifdef MDS_GEMM_TRACE
+#define GT_TRACE(T_, ev_) do { if (p.trace && blockIdx.x == 0 && (T_) < 64 && (threadIdx.x & 31) == 0) p.trace[(T_) * 16 + (ev_)] = clock64(); } while (0)
+#else
+#define GT_TRACE(T_, ev_) do { } while (0)
+#endif
+
 constexpr int kTcBM = 128, kTcBK = 64, kTcMaxKB = 3;
 constexpr int kTcEpiWarps = 16;
-constexpr int kGP = 3;                 // 16-column groups an epilogue warp holds in registers at once
 constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 constexpr int kTcABytes = kTcBM * kTcBK * 2;          // 16 KB per K block
 constexpr int kTcMaxGateK = 1152;                     // largest gated K (blocks.5.x conv_pwl)
@@ -76,7 +82,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded spin: a protocol bug must surface as a trap (-> CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();
+        if (spins > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
@@ -137,6 +143,7 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) 
                  : "memory");
 }
 
+template <bool ACT, bool RES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBias, TcGemmParams p) {
@@ -266,12 +273,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!p.streamed) mbar_wait(&a_full[ab], ((uint32_t)i >> 1) & 1);
                 for (int nt = 0; nt < p.n_tiles; ++nt, ++t) {
                     const int acc = t & 1;
+                    GT_TRACE(t, 0);
                     mbar_wait(&acc_empty[acc], (((uint32_t)t >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                     tc_fence_after();
+                    GT_TRACE(t, 1);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                     for (int kb = 0; kb <= num_kb; ++kb) {
                         mbar_wait(gated ? &a_gated[stage] : &b_full[stage], phase);
                         tc_fence_after();
+                        if (kb < 4) GT_TRACE(t, 2 + kb);
                         const bool bias_blk = kb == num_kb;
                         unsigned char* st = s_ring + (size_t)stage * stage_bytes;
                         const unsigned char* a_src = bias_blk ? s_ones : (p.streamed ? st : s_a + (size_t)(ab * kTcMaxKB + kb) * kTcABytes);
@@ -291,6 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
+                    GT_TRACE(t, 6);
                 }
                 if (!p.streamed) {
                     if (elect_one()) tc_commit(&a_empty[ab]);            // every MMA that reads this A tile has been issued
@@ -352,14 +363,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ================= epilogue (warps 2..17; gated mode: warps 2..9) =================
-        // Two groups of 8 warps; group e drains accumulator e (tiles t with t % 2 == e), so the TMEM reads and stores of
-        // one tile overlap the bias/SiLU math of the other.  TMEM lane quadrant = warp % 4; the two warps of a group
-        // that share a quadrant take alternate 16-column groups.
+        // Two groups of 8 warps; group e drains accumulator e (tiles t with t % 2 == e).  TMEM lane quadrant = warp % 4; the two
+        // warps of a group that share a quadrant take alternate 16-column chunks.  A warp streams its chunks: the tcgen05.ld (and
+        // the residual load) of chunk k+1 is in flight while chunk k goes through bias-free SiLU (four values per reciprocal),
+        // one rounding to fp16 and one 32-byte store.  Only two 16-register buffers are live, so the compiler can interleave the
+        // 16 independent SiLU chains of a chunk (with three chunks in registers and the 96-register cap of a 576-thread CTA it
+        // serialised them: ~100 clocks per element, measured with clock64 stamps, tools/conv_trace.sh).
         const int q = warp & 3;
         const int e = ((warp - 2) >> 2) & 1;
         const int half = (warp - 2) >> 3;              // 0 in gated mode (8 epilogue warps: one per quadrant and accumulator)
         const int nhalf = gated ? 1 : 2;
         const int ngroups = p.BN >> 4;
+        const int nk = (ngroups - half + nhalf - 1) / nhalf;      // chunks of this warp per tile
         int t = 0;
         for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
             long long row;
@@ -373,60 +388,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row = (long long)mt * kTcBM + q * 32 + lane;
                 row_ok = row < p.M;
             }
-            __half* c_row = p.C + row * p.N;
-            const __half* r_row = p.res + row * p.N;
             for (int nt = 0; nt < p.n_tiles; ++nt, ++t) {
                 if ((t & 1) != e) continue;
-                const int n0 = nt * p.BN;
-                const bool has_res = p.res != nullptr;
-                for (int g0 = half; g0 < ngroups; g0 += nhalf * kGP) {   // up to kGP column groups (48 accumulator columns) per pass
-                    uint32_t rv[kGP][8];
-                    if (has_res) {       // residual loads are issued before waiting for the accumulator
+                __half* c_ptr = p.C + row * p.N + nt * p.BN + half * 16;
+                const __half* r_ptr = p.res + row * p.N + nt * p.BN + half * 16;
+                const uint32_t t_col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e * p.BN + half * 16);
+                uint32_t va[16], vb[16], ra[8], rb[8];
+                // chunk k: columns [16 * (half + nhalf * k), + 16) of the tile
+                auto request = [&](int k, uint32_t (&v)[16], uint32_t (&r)[8]) {
+                    if constexpr (RES) {
+                        if (row_ok) ld_global_v8(r_ptr + k * nhalf * 16, r);
+                    }
+                    tc_ld16(t_col + (uint32_t)(k * nhalf * 16), v);
+                };
+                auto consume = [&](int k, uint32_t (&v)[16], uint32_t (&r)[8]) {
+                    uint32_t pk[8];
 #pragma unroll
-                        for (int j = 0; j < kGP; ++j) {
-                            const int g = g0 + nhalf * j;
-                            if (g < ngroups && row_ok) ld_global_v8(r_row + n0 + g * 16, rv[j]);
+                    for (int h = 0; h < 4; ++h) {
+                        float x[4] = {__uint_as_float(v[4 * h]), __uint_as_float(v[4 * h + 1]), __uint_as_float(v[4 * h + 2]),
+                                      __uint_as_float(v[4 * h + 3])};
+                        if constexpr (ACT) silu4(x);
+                        if constexpr (RES) {
+                            const float2 r01 = unpack_half2(r[2 * h]), r23 = unpack_half2(r[2 * h + 1]);
+                            x[0] += r01.x; x[1] += r01.y; x[2] += r23.x; x[3] += r23.y;
                         }
+                        pk[2 * h] = pack_half2(x[0], x[1]);
+                        pk[2 * h + 1] = pack_half2(x[2], x[3]);
                     }
-                    if (g0 == half) {
-                        mbar_wait(&acc_full[e], ((uint32_t)t >> 1) & 1);
-                        tc_fence_after();
-                    }
-                    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(e * p.BN);
-                    uint32_t v[kGP][16];
-#pragma unroll
-                    for (int j = 0; j < kGP; ++j) {
-                        const int g = g0 + nhalf * j;
-                        if (g < ngroups) tc_ld16(t_row + (uint32_t)(g * 16), v[j]);
-                    }
-                    tc_wait_ld();
-                    if (g0 + nhalf * kGP >= ngroups) {
-                        // last TMEM read of this tile: hand the accumulator back before doing the math / stores
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[e]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < kGP; ++j) {
-                        const int g = g0 + nhalf * j;
-                        if (g < ngroups) {
-                            uint32_t pk[8];
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                float x0 = __uint_as_float(v[j][4 * h]), x1 = __uint_as_float(v[j][4 * h + 1]);
-                                float x2 = __uint_as_float(v[j][4 * h + 2]), x3 = __uint_as_float(v[j][4 * h + 3]);
-                                if (p.act) { x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3); }
-                                if (has_res && row_ok) {
-                                    const float2 r01 = unpack_half2(rv[j][2 * h]), r23 = unpack_half2(rv[j][2 * h + 1]);
-                                    x0 += r01.x; x1 += r01.y; x2 += r23.x; x3 += r23.y;
-                                }
-                                pk[2 * h] = pack_half2(x0, x1);
-                                pk[2 * h + 1] = pack_half2(x2, x3);
-                            }
-                            if (row_ok) st_global_v8(c_row + n0 + g * 16, pk);
+                    if (row_ok) st_global_v8(c_ptr + k * nhalf * 16, pk);
+                };
+                auto release = [&]() {       // last TMEM read of this tile is in registers: hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[e]);
+                };
+                if (warp == 2 || warp == 6) GT_TRACE(t, 8);
+                mbar_wait(&acc_full[e], ((uint32_t)t >> 1) & 1);
+                tc_fence_after();
+                if (warp == 2 || warp == 6) GT_TRACE(t, 9);
+                request(0, va, ra);
+                tc_wait_ld();
+                if (warp == 2 || warp == 6) GT_TRACE(t, 10);
+                if (nk == 1) release();
+                for (int k = 0; k < nk; k += 2) {
+                    if (k + 1 < nk) request(k + 1, vb, rb);
+                    consume(k, va, ra);
+                    if (k + 1 < nk) {
+                        tc_wait_ld();
+                        if (k + 2 == nk) release();
+                        if (k + 2 < nk) request(k + 2, va, ra);
+                        consume(k + 1, vb, rb);
+                        if (k + 2 < nk) {
+                            tc_wait_ld();
+                            if (k + 3 == nk) release();
                         }
                     }
                 }
+                if (warp == 2 || warp == 6) GT_TRACE(t, 12);
             }
         }
     }

@@ -262,10 +262,10 @@ static int launch_conv3_tc(const __half* in, __half* out, const __half* w1, cons
 
 // every dense 3x3 block on tcgen05 (conv_tc.cuh): halo tiles through 5-D tensor maps over NHWC seen as [n][C/8][H][W][8];
 // stride 2 reads the four (row, column) parity phases of the input through four maps
-template <int CIN, int CMID, int CPROJ, int STRIDE, bool RES, int TH, bool PT, int MINB>
+template <int CIN, int CMID, int CPROJ, int STRIDE, bool RES, int TH, bool PT, int MINB, bool FOLD = false>
 static int launch_conv_tc(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2, const float* b2,
                           int n, int H, int W, cudaStream_t st) {
-    using Cfg = ConvTcCfg<CIN, CMID, CPROJ, STRIDE, RES, TH, PT>;
+    using Cfg = ConvTcCfg<CIN, CMID, CPROJ, STRIDE, RES, TH, PT, FOLD>;
     auto enc = tensor_map_encoder();
     if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     if (STRIDE == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv_tc: stride-2 input must be even");
@@ -289,15 +289,37 @@ static int launch_conv_tc(const __half* in, __half* out, const __half* w1, const
     p.Ho = H / STRIDE; p.Wo = W / STRIDE;
     p.tiles_x = (p.Wo + Cfg::TW - 1) / Cfg::TW;
     p.tiles_y = (p.Ho + Cfg::TH - 1) / Cfg::TH;
+    p.trace = nullptr;
+#ifdef MDS_CONV_TRACE
+    static long long* tr = nullptr;
+    if (!tr) cudaMalloc(&tr, 64 * 16 * sizeof(long long));
+    cudaMemsetAsync(tr, 0, 64 * 16 * sizeof(long long), st);
+    p.trace = tr;
+#endif
     const long long tiles = (long long)p.tiles_x * p.tiles_y * n;
     if (tiles <= 0) return MDS_OK;
-    auto kern = conv_tc_kernel<CIN, CMID, CPROJ, STRIDE, RES, TH, PT, MINB>;
+    auto kern = conv_tc_kernel<CIN, CMID, CPROJ, STRIDE, RES, TH, PT, MINB, FOLD>;
     ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
     int grid = num_sms() * MINB;
     if (tiles < grid) grid = (int)tiles;
     ProfScope ps(MDS_KIND_CONV3X3, st);
     launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, maps, p);
     LAUNCH_CHECK("conv_tc");
+#ifdef MDS_CONV_TRACE
+    {   // columns: MMA warp 0 loop top, 1 D1 free, 2 conv MMAs issued, 3 before tile wait, 4 proj start, 5 P ready, 6 D2 free, 7 proj issued;
+        // epilogue warp 2: 8 before D1 wait, 9 D1 ready, 10 E1 start, 11 E1 done, 12 next chunk requested, 13 E2(prev) done, 14 D2 ready
+        static long long h[64 * 16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[3] ? h[3] : h[0];
+        fprintf(stderr, "TRACE cin=%d cmid=%d stride=%d\n", CIN, CMID, STRIDE);
+        for (int t = 0; t < 40; ++t) {
+            fprintf(stderr, "T%02d", t);
+            for (int e = 0; e < 15; ++e) fprintf(stderr, " %6lld", h[t * 16 + e] ? h[t * 16 + e] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     return MDS_OK;
 }
 
@@ -315,7 +337,9 @@ static int launch_conv3(const __half* in, __half* out, const __half* w1, const f
     if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0))                          \
         return pt ? launch_conv_tc<CI, CM, CP, S, R, TH_T, true, MB>(in, out, w1, b1, w2, b2, n, H, W, st)   \
                   : launch_conv_tc<CI, CM, CP, S, R, TH_S, false, MB>(in, out, w1, b1, w2, b2, n, H, W, st);
-        CTCASE(32, 16, 0, 1, false, 15, 15, 2)     // blocks.0.0  ConvBnAct: two CTAs per SM
+        if (cin == 32 && cmid == 16 && stride == 1 && cproj == 0 && res == 0)      // blocks.0.0 ConvBnAct: two CTAs per SM
+            return pt ? launch_conv_tc<32, 16, 0, 1, false, 16, true, 2, true>(in, out, w1, b1, w2, b2, n, H, W, st)     // column taps folded into N
+                      : launch_conv_tc<32, 16, 0, 1, false, 15, false, 2, false>(in, out, w1, b1, w2, b2, n, H, W, st);
         CTCASE(16, 64, 32, 2, false, 15, 15, 1)    // blocks.1.0  EdgeResidual s2
         CTCASE(32, 128, 32, 1, true, 15, 15, 1)    // blocks.1.1
         CTCASE(32, 128, 48, 2, false, 3, 7, 1)     // blocks.2.0  (P in shared memory only fits with 3-row tiles)
@@ -392,20 +416,46 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     p.stages = tc_stages(p.BN, p.streamed);
     const size_t smem = tc_smem_bytes(p.BN, p.streamed);
     if (smem > 227 * 1024) return fail(MDS_ERR_INVALID, "gemm_tc: BN=%d needs %zu bytes of shared memory", p.BN, smem);
-    {   // the opt-in limit is a per-device attribute: track the largest value set on each device
-        static size_t smem_set[kMaxDevices] = {};
+    const bool act = p.act != 0, res = p.res != nullptr;
+    auto kern = act ? (res ? gemm_tc_kernel<true, true> : gemm_tc_kernel<true, false>)
+                    : (res ? gemm_tc_kernel<false, true> : gemm_tc_kernel<false, false>);
+    {   // the opt-in limit is a per-device attribute of each instantiation: track the largest value set on each device
+        static size_t smem_set[4][kMaxDevices] = {};
+        const int ki = (act ? 2 : 0) + (res ? 1 : 0);
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev >= 0 && dev < kMaxDevices && smem > smem_set[dev]) {
-            CUDA_TRY(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set[dev] = smem;
+        if (dev >= 0 && dev < kMaxDevices && smem > smem_set[ki][dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[ki][dev] = smem;
         }
     }
     int grid = num_sms();
     if (p.m_tiles < grid) grid = p.m_tiles;
+    p.trace = nullptr;
+#ifdef MDS_GEMM_TRACE
+    static long long* tr = nullptr;
+    if (!tr) cudaMalloc(&tr, 64 * 16 * sizeof(long long));
+    cudaMemsetAsync(tr, 0, 64 * 16 * sizeof(long long), st);
+    p.trace = tr;
+#endif
     ProfScope ps(MDS_KIND_GEMM1X1, st);
-    launch_pdl(gemm_tc_kernel, dim3(grid), dim3(kTcThreads), smem, st, tmA, tmB, tmBias, p);
+    launch_pdl(kern, dim3(grid), dim3(kTcThreads), smem, st, tmA, tmB, tmBias, p);
     LAUNCH_CHECK("gemm_tc");
+#ifdef MDS_GEMM_TRACE
+    {   // per accumulator tile t.  MMA warp: 0 loop top, 1 accumulator free, 2-5 k-block 0-3 in smem, 6 all MMAs issued;
+        // epilogue warps 2 / 6 (group 0 / 1): 8 before acc_full, 9 accumulator ready, 10 first TMEM pass loaded, 11 last pass loaded, 12 done
+        static long long h[64 * 16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        fprintf(stderr, "GTRACE N=%d K=%d BN=%d streamed=%d act=%d m_tiles=%d n_tiles=%d\n", p.N, p.K, p.BN, p.streamed, p.act, p.m_tiles, p.n_tiles);
+        for (int t = 0; t < 24; ++t) {
+            fprintf(stderr, "T%02d", t);
+            for (int e = 0; e < 13; ++e) fprintf(stderr, " %6lld", h[t * 16 + e] ? h[t * 16 + e] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     return MDS_OK;
 }
 
