@@ -176,11 +176,14 @@ __global__ void __launch_bounds__(256, 3) dwconv_tma_kernel(const __grid_constan
 
     auto emit = [&](float2 (&acc)[kDtPXW]) {           // emits one output row and re-arms the accumulators with the bias
 #pragma unroll
+        for (int j = 0; j < kDtPXW; ++j) {           // all SiLU chains first, unconditionally: independent, so they interleave
+            acc[j] = dt_silu2(acc[j]);               // (a branch per pixel serialised them: ~6 dependent SFU / FMA steps each)
+        }
+#pragma unroll
         for (int j = 0; j < kDtPXW; ++j) {
             if (j < npx) {
-                const float2 o = dt_silu2(acc[j]);
-                lsum = __fadd2_rn(lsum, o);
-                *reinterpret_cast<uint32_t*>(o_ptr + j * p.C) = pack_half2(o.x, o.y);
+                lsum = __fadd2_rn(lsum, acc[j]);
+                *reinterpret_cast<uint32_t*>(o_ptr + j * p.C) = pack_half2(acc[j].x, acc[j].y);
             }
             acc[j] = bias;
         }
