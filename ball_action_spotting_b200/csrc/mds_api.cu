@@ -16,6 +16,7 @@
 #include "conv3x3.cuh"
 #include "conv3x3_tc.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc_ws.cuh"
 #include "dwconv.cuh"
 #include "dwconv_tma.cuh"
 #include "gemm1x1.cuh"
@@ -323,9 +324,52 @@ static int launch_conv_tc(const __half* in, __half* out, const __half* w1, const
     return MDS_OK;
 }
 
+// blocks.2.1 on tcgen05 with the 3x3 weights streamed from L2 (conv_tc_ws.cuh).  w1t = the tap-major copy of w1 made by
+// conv_w1_tapmajor_kernel (the handle keeps one per block; the stand-alone entry point repacks into a per-thread scratch buffer).
+template <int CIN, int CMID, int CPROJ>
+static int launch_conv_tc_ws(const __half* in, __half* out, const __half* w1, const __half* w1t, const float* b1, const __half* w2,
+                             const float* b2, int n, int H, int W, cudaStream_t st) {
+    using Cfg = ConvWsCfg<CIN, CMID, CPROJ>;
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    if (w1t == nullptr) {
+        static thread_local __half* scratch[kMaxDevices] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= kMaxDevices) return fail(MDS_ERR_INVALID, "conv_tc_ws: device index");
+        if (!scratch[dev]) CUDA_TRY(cudaMalloc(&scratch[dev], (size_t)9 * CIN * CMID * sizeof(__half)));
+        conv_w1_tapmajor_kernel<<<64, 256, 0, st>>>(w1, scratch[dev], CIN, CMID);
+        LAUNCH_CHECK("conv_w1_tapmajor");
+        w1t = scratch[dev];
+    }
+    CUtensorMap tm;
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(CIN / 8), (cuuint64_t)n};
+    cuuint64_t strides[4] = {(cuuint64_t)CIN * 2, (cuuint64_t)W * CIN * 2, 16, (cuuint64_t)H * W * CIN * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)Cfg::PW, (cuuint32_t)Cfg::PH, (cuuint32_t)(CIN / 8), 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled(conv_tc_ws) failed (%d) n=%d H=%d W=%d C=%d", (int)r, n, H, W, CIN);
+    ConvWsParams p;
+    p.in = in; p.out = out; p.w1t = w1t; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.n = n; p.H = H; p.W = W;
+    p.tiles_x = (W + Cfg::TW - 1) / Cfg::TW;
+    p.tiles_y = (H + Cfg::TH - 1) / Cfg::TH;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * n;
+    if (tiles <= 0) return MDS_OK;
+    auto kern = conv_tc_ws_kernel<CIN, CMID, CPROJ>;
+    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
+    int grid = num_sms();
+    if (tiles < grid) grid = (int)tiles;
+    ProfScope ps(MDS_KIND_CONV3X3, st);
+    launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, tm, p);
+    LAUNCH_CHECK("conv_tc_ws");
+    return MDS_OK;
+}
+
 static int launch_conv3(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2,
                         const float* b2, int n, int H, int W, int cin, int cmid, int stride, int cproj, int res,
-                        cudaStream_t st) {
+                        cudaStream_t st, const __half* w1t = nullptr) {
     Conv3Params p;
     p.in = in; p.out = out; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
     p.n = n; p.H = H; p.W = W;
@@ -344,6 +388,8 @@ static int launch_conv3(const __half* in, __half* out, const __half* w1, const f
         CTCASE(32, 128, 32, 1, true, 15, 15, 1)    // blocks.1.1
         CTCASE(32, 128, 48, 2, false, 3, 7, 1)     // blocks.2.0  (P in shared memory only fits with 3-row tiles)
 #undef CTCASE
+        if (pt && cin == 48 && cmid == 192 && stride == 1 && cproj == 48 && res == 1)      // blocks.2.1: 3x3 weights streamed from L2
+            return launch_conv_tc_ws<48, 192, 48>(in, out, w1, w1t, b1, w2, b2, n, H, W, st);
     }
     if (cin == 32 && cmid == 128 && stride == 1 && cproj == 32 && res == 1)     // blocks.1.1: tcgen05 implicit GEMM
         return launch_conv3_tc<32, 128, 32>(in, out, w1, b1, w2, b2, n, H, W, st);
@@ -857,7 +903,7 @@ struct Block2d {
     char kind;   // 'c' ConvBnAct, 'e' EdgeResidual, 'i' InvertedResidual
     int cin, mid, cout, stride, rd;
     bool skip;
-    const __half *w1 = nullptr, *w2 = nullptr, *wpw = nullptr, *wpwl = nullptr, *bmpw = nullptr, *bmpwl = nullptr;
+    const __half *w1 = nullptr, *w1t = nullptr, *w2 = nullptr, *wpw = nullptr, *wpwl = nullptr, *bmpw = nullptr, *bmpwl = nullptr;
     const float *b1 = nullptr, *b2 = nullptr, *bpw = nullptr, *bpwl = nullptr;
     const float *wdw = nullptr, *bdw = nullptr, *se_w1 = nullptr, *se_b1 = nullptr, *se_w2t = nullptr, *se_b2 = nullptr, *w32pwl = nullptr;
 };
@@ -998,6 +1044,20 @@ extern "C" int mds_weights_commit(MdsHandle* h) {
                 TRY(get_tensor(h, p + "c3.b", b.mid, &b.b1));
                 TRY(get_tensor(h, p + "pwl.w", (size_t)b.cout * b.mid, &b.w2));
                 TRY(get_tensor(h, p + "pwl.b", b.cout, &b.b2));
+                if (b.cin == 48 && b.mid == 192 && b.stride == 1) {      // conv_tc_ws_kernel streams a tap-major copy of the 3x3 weights
+                    DevBuf& wt = h->tensors[p + "c3.wt"];
+                    const size_t bytes = (size_t)b.mid * 9 * b.cin * sizeof(__half);
+                    if (wt.bytes != bytes) {
+                        if (wt.ptr) cudaFree(wt.ptr);
+                        wt.ptr = nullptr; wt.bytes = 0;
+                        CUDA_TRY(cudaMalloc(&wt.ptr, bytes));
+                        wt.bytes = bytes;
+                    }
+                    conv_w1_tapmajor_kernel<<<64, 256>>>(b.w1, reinterpret_cast<__half*>(wt.ptr), b.cin, b.mid);
+                    CUDA_TRY(cudaGetLastError());
+                    CUDA_TRY(cudaDeviceSynchronize());
+                    b.w1t = reinterpret_cast<const __half*>(wt.ptr);
+                }
             } else {
                 TRY(get_tensor(h, p + "pw.w", (size_t)b.mid * b.cin, &b.wpw));
                 TRY(get_tensor(h, p + "pw.b", b.mid, &b.bpw));
@@ -1177,7 +1237,7 @@ static int forward_2d_impl(MdsHandle* h, const MdsFrames& fr, int n_images, __ha
             if (b.kind == 'c') {
                 TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, nullptr, nullptr, cs, hh, ww, b.cin, b.cout, b.stride, 0, 0, st));
             } else if (b.kind == 'e') {
-                TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, b.w2, b.b2, cs, hh, ww, b.cin, b.mid, b.stride, b.cout, b.skip, st));
+                TRY(launch_conv3(X[cur], X[cur ^ 1], b.w1, b.b1, b.w2, b.b2, cs, hh, ww, b.cin, b.mid, b.stride, b.cout, b.skip, st, b.w1t));
             } else {
                 TRY(launch_gemm(X[cur], b.wpw, b.bpw, nullptr, nullptr, M1, (long long)hh * ww, cs, b.mid, b.cin, 1, st, b.bmpw));
                 if (g_tail_mode == 1) {
