@@ -24,6 +24,7 @@
 #include "mbconv_tail.cuh"
 #include "se_head.cuh"
 #include "stem.cuh"
+#include "stem_tc.cuh"
 #include "train.cuh"
 #include "postproc.cuh"
 
@@ -205,6 +206,34 @@ static int launch_stem(const MdsFrames& f, int n, const __half* wh, const float*
     p.stored_h = f.stored_h; p.pad_top = f.pad_top; p.H = f.H; p.W = f.W; p.hflip = f.hflip;
     p.scale = f.dtype == 0 ? 1.0f / 255.0f : 1.0f;
     p.wh = wh; p.bias = bias; p.out = out;
+    // uint8 frames: TMA + tcgen05 stem (stem_tc.cuh); conv mode 0 and float input keep the mma.sync kernel
+    if (f.dtype == 0 && g_conv_mode >= 1 && f.W >= kStcIW && f.W % 16 == 0 && f.plane_stride % 16 == 0 && f.img_stride % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(f.data) & 15) == 0 && f.stored_h >= 1) {
+        auto enc = tensor_map_encoder();
+        if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        CUtensorMap tm;
+        cuuint64_t dims[4] = {(cuuint64_t)f.W, (cuuint64_t)f.stored_h, 3, (cuuint64_t)n};
+        cuuint64_t strides[3] = {(cuuint64_t)f.W, (cuuint64_t)f.plane_stride, (cuuint64_t)f.img_stride};
+        cuuint32_t box[4] = {(cuuint32_t)kStcIW, (cuuint32_t)kStcIH, 3, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(f.data), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled(stem) failed (%d) n=%d stored_h=%d W=%d", (int)r, n, f.stored_h, f.W);
+        StemTcParams q;
+        q.n = n; q.H = f.H; q.W = f.W; q.Ho = f.H / 2; q.Wo = f.W / 2; q.pad_top = f.pad_top; q.hflip = f.hflip;
+        q.scale = 1.0f / 255.0f; q.wh = wh; q.bias = bias; q.out = out;
+        q.tiles_x = (q.Wo + kStcTW - 1) / kStcTW; q.tiles_y = (q.Ho + kStcTH - 1) / kStcTH;
+        const long long tiles = (long long)q.tiles_x * q.tiles_y * n;
+        ENSURE_SMEM_ATTR(stem_tc_kernel, kStcSmem);
+        int grid = 2 * num_sms();
+        if (tiles < grid) grid = (int)tiles;
+        ProfScope ps(MDS_KIND_STEM, st);
+        launch_pdl(stem_tc_kernel, dim3(grid), dim3(kStcThreads), kStcSmem, st, tm, q);
+        LAUNCH_CHECK("stem_tc");
+        return MDS_OK;
+    }
     dim3 grid((f.W / 2 + kStemTW - 1) / kStemTW, (f.H / 2 + kStemTH - 1) / kStemTH, n);
     ProfScope ps(MDS_KIND_STEM, st);
     if (f.dtype == 0) launch_pdl(stem_kernel<uint8_t>, grid, dim3(256), 0, st, p);

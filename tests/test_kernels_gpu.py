@@ -39,16 +39,23 @@ def nchw(t):
 
 
 @pytest.mark.parametrize("dtype,hflip", [("u8", 0), ("u8", 1), ("f32", 0)])
-def test_stem(lib, dtype, hflip):
+@pytest.mark.parametrize("mode", [2, 0])
+@pytest.mark.parametrize("size", [(2, 96, 160, 80), (2, 736, 1280, 720), (3, 64, 208, 50)])
+def test_stem(lib, dtype, hflip, mode, size):
+    """mode 2: uint8 frames go through stem_tc_kernel (TMA + tcgen05); mode 0 and float input: the mma.sync stem_kernel.
+    Sizes: a small case, the real 720 -> 736 x 1280 frames (every persistent CTA loops over many tiles), and a width / height
+    that is not a multiple of the 64 x 8 output tile with an odd number of stored rows."""
     from ball_action_spotting_b200._lib import MdsFrames
-    n, H, W = 2, 96, 160
+    n, H, W, sh = size
     w = torch.randn(32, 3, 3, 3, generator=gen(1)) * 0.3
     b = torch.randn(32, generator=gen(2)) * 0.1
     if dtype == "u8":
-        raw = torch.randint(0, 256, (n, 3, 80, W), dtype=torch.uint8, generator=gen(3))
+        raw = torch.randint(0, 256, (n, 3, sh, W), dtype=torch.uint8, generator=gen(3))
         x = O.pad_normalize(raw, (W, H))
-        dt, stored_h = 0, 80
+        dt, stored_h = 0, sh
     else:
+        if H > 100:
+            pytest.skip("float input: small case only")
         raw = torch.rand((n, 3, H, W), generator=gen(3))
         x = raw
         dt, stored_h = 1, H
@@ -59,10 +66,14 @@ def test_stem(lib, dtype, hflip):
     from ball_action_spotting_b200.packer import stem_weights
     d_w = stem_weights(w).to(DEV)
     d_b = b.to(DEV)
-    out = torch.empty((n, H // 2, W // 2, 32), dtype=torch.float16, device=DEV)
+    out = torch.full((n, H // 2, W // 2, 32), float("nan"), dtype=torch.float16, device=DEV)
     fr = MdsFrames(d_raw.data_ptr(), dt, 3 * stored_h * W, stored_h * W, stored_h, (H - stored_h) // 2, H, W, hflip)
-    ok(lib.mds_k_stem(C.byref(fr), n, d_w.data_ptr(), d_b.data_ptr(), out.data_ptr(), None), lib)
-    torch.cuda.synchronize()
+    ok(lib.mds_set_conv_mode(mode), lib)
+    try:
+        ok(lib.mds_k_stem(C.byref(fr), n, d_w.data_ptr(), d_b.data_ptr(), out.data_ptr(), None), lib)
+        torch.cuda.synchronize()
+    finally:
+        lib.mds_set_conv_mode(2)
     assert rel(nchw(out), ref) <= TOL
 
 
