@@ -318,7 +318,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, ConvTcParams p) {
                             }
                         } else {
 #pragma unroll
-                        for (int rs = 0; rs < 9; ++rs) {
+                        for (int rsi = 0; rsi < 9; ++rsi) {
+                            const int rs = (MDS_NUMERICS_VARIANT & 2) ? 8 - rsi : rsi;
                             const int r = rs / 3, s = rs - r * 3;
                             const int phase = STRIDE == 1 ? 0 : (r & 1) * 2 + (s & 1);
                             const int off = STRIDE == 1 ? r * Cfg::PW + s : (r >> 1) * Cfg::PW + (s >> 1);

@@ -292,8 +292,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tc_mma_f16(d_tmem, adesc, bdesc, idesc, kb != 0);
                             } else {
 #pragma unroll
-                                for (int k = 0; k < kTcBK / 16; ++k)     // advance 16 K-elements = 32 B inside the swizzle atom (>>4 = 2)
-                                    tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                                for (int ki = 0; ki < kTcBK / 16; ++ki) {     // advance 16 K-elements = 32 B inside the swizzle atom (>>4 = 2)
+                                    const int k = (MDS_NUMERICS_VARIANT & 4) ? kTcBK / 16 - 1 - ki : ki;
+                                    tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | ki) != 0);
+                                }
                             }
                             tc_commit(&b_empty[stage]);                  // stage reusable once these MMAs have read it
                             if (bias_blk) tc_commit(&acc_full[acc]);     // accumulator complete

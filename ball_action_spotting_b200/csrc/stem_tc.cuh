@@ -148,11 +148,13 @@ __global__ void __launch_bounds__(kStcThreads, 2) stem_tc_kernel(const __grid_co
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
-                    for (int part = 0; part < 2; ++part)
+                    for (int pi = 0; pi < 2; ++pi)
 #pragma unroll
-                        for (int kc = 0; kc < 3; ++kc)
+                        for (int kc = 0; kc < 3; ++kc) {
+                            const int part = (MDS_NUMERICS_VARIANT & 1) ? 1 - pi : pi;
                             tc_mma_f16(tmem_base + d * 32, tc_desc_nosw(aa + slot * kStcABytes + kc * 2 * 2048, 2048),
-                                       tc_desc_nosw(wa + part * kStcWBytes + kc * 2 * 512, 512), idesc, (part | kc) != 0);
+                                       tc_desc_nosw(wa + part * kStcWBytes + kc * 2 * 512, 512), idesc, (pi | kc) != 0);
+                        }
                     tc_commit(&a_empty[slot]);
                     tc_commit(&d_full[d]);
                 }
