@@ -23,7 +23,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "conv3x3_tc.cuh"
+#include "tc_helpers.cuh"
 #include "gemm_tc.cuh"
 
 // Timeline instrumentation, compiled out of the product build (tools/conv_trace.sh builds a separate library with it)

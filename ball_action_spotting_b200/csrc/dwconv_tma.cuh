@@ -18,7 +18,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "conv3x3_tc.cuh"
+#include "tc_helpers.cuh"
 #include "gemm_tc.cuh"
 
 namespace mds {

@@ -13,8 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
-#include "conv3x3.cuh"
-#include "conv3x3_tc.cuh"
+#include "tc_helpers.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc_ws.cuh"
 #include "dwconv.cuh"
@@ -148,13 +147,14 @@ extern "C" int mds_set_tail_mode(int mode) {
     g_tail_mode = mode;
     return MDS_OK;
 }
-// Dense 3x3 blocks (blocks.0.0 - 2.1), selectable for A/B measurements (all parity-tested):
-//   2 (default): conv_tc_kernel (TMA + tcgen05, expanded tensor kept in tensor memory) for blocks.0.0 / 1.0 / 1.1 / 2.0
-//   1: conv_tc_kernel with the expanded tensor staged in shared memory
-//   0: round-1 kernels (mma.sync conv3x3_kernel; conv3x3_tc_kernel for blocks.1.1)
+// Dense 3x3 blocks (blocks.0.0 - 2.0), selectable for A/B measurements (both parity-tested):
+//   2 (default): conv_tc_kernel keeps the expanded tensor in tensor memory (A operand of the projection from TMEM); blocks.0.0
+//                with the column taps folded into N
+//   1: conv_tc_kernel stages the expanded tensor in shared memory; blocks.0.0 without the fold
+// blocks.2.1 (conv_tc_ws_kernel) and the stem (stem_tc_kernel) have one implementation.  The round-1 mma.sync kernels are gone.
 static int g_conv_mode = getenv("MDS_CONV_MODE") ? atoi(getenv("MDS_CONV_MODE")) : 2;
 extern "C" int mds_set_conv_mode(int mode) {
-    if (mode < 0 || mode > 2) return fail(MDS_ERR_INVALID, "conv mode must be 0..2");
+    if (mode < 1 || mode > 2) return fail(MDS_ERR_INVALID, "conv mode must be 1 or 2");
     g_conv_mode = mode;
     return MDS_OK;
 }
@@ -206,9 +206,12 @@ static int launch_stem(const MdsFrames& f, int n, const __half* wh, const float*
     p.stored_h = f.stored_h; p.pad_top = f.pad_top; p.H = f.H; p.W = f.W; p.hflip = f.hflip;
     p.scale = f.dtype == 0 ? 1.0f / 255.0f : 1.0f;
     p.wh = wh; p.bias = bias; p.out = out;
-    // uint8 frames: TMA + tcgen05 stem (stem_tc.cuh); conv mode 0 and float input keep the mma.sync kernel
-    if (f.dtype == 0 && g_conv_mode >= 1 && f.W >= kStcIW && f.W % 16 == 0 && f.plane_stride % 16 == 0 && f.img_stride % 16 == 0 &&
-        (reinterpret_cast<uintptr_t>(f.data) & 15) == 0 && f.stored_h >= 1) {
+    // uint8 frames (the path of the predictor, the sweep and bench.py): TMA + tcgen05 stem (stem_tc.cuh).  Float input (the nn.Module
+    // called with already normalised frames) keeps the mma.sync gather kernel of stem.cuh.
+    if (f.dtype == 0) {
+        if (f.W < kStcIW || f.W % 16 || f.plane_stride % 16 || f.img_stride % 16 || (reinterpret_cast<uintptr_t>(f.data) & 15) || f.stored_h < 1)
+            return fail(MDS_ERR_INVALID, "stem: uint8 frames need W >= %d, W / plane / image strides multiples of 16 and a 16-byte aligned base "
+                        "(W=%d plane_stride=%lld img_stride=%lld)", kStcIW, f.W, (long long)f.plane_stride, (long long)f.img_stride);
         auto enc = tensor_map_encoder();
         if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
         CUtensorMap tm;
@@ -236,57 +239,9 @@ static int launch_stem(const MdsFrames& f, int n, const __half* wh, const float*
     }
     dim3 grid((f.W / 2 + kStemTW - 1) / kStemTW, (f.H / 2 + kStemTH - 1) / kStemTH, n);
     ProfScope ps(MDS_KIND_STEM, st);
-    if (f.dtype == 0) launch_pdl(stem_kernel<uint8_t>, grid, dim3(256), 0, st, p);
-    else if (f.dtype == 1) launch_pdl(stem_kernel<float>, grid, dim3(256), 0, st, p);
+    if (f.dtype == 1) launch_pdl(stem_kernel<float>, grid, dim3(256), 0, st, p);
     else return fail(MDS_ERR_INVALID, "stem: dtype must be 0 (uint8) or 1 (float32)");
     LAUNCH_CHECK("stem");
-    return MDS_OK;
-}
-
-template <int CIN, int CMID, int STRIDE, int CPROJ, bool RES, int MINB, int MT>
-static int launch_conv3_t(const Conv3Params& p, cudaStream_t st) {
-    using Cfg = Conv3Cfg<CIN, CMID, STRIDE, CPROJ, RES>;
-    auto kern = conv3x3_kernel<CIN, CMID, STRIDE, CPROJ, RES, MINB, MT>;
-    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
-    const int tiles = ((p.Wo + Cfg::TW - 1) / Cfg::TW) * ((p.Ho + Cfg::TH - 1) / Cfg::TH) * p.n;
-    if (tiles <= 0) return MDS_OK;
-    int grid = num_sms() * MINB;
-    if (grid > tiles) grid = tiles;
-    ProfScope ps(MDS_KIND_CONV3X3, st);
-    launch_pdl(kern, dim3(grid), dim3(256 / MT), Cfg::SMEM, st, p);
-    LAUNCH_CHECK("conv3x3");
-    return MDS_OK;
-}
-
-// stride-1 FusedMBConv on tcgen05 (conv3x3_tc.cuh): halo tiles through a 5-D tensor map over NHWC seen as [n][C/8][H][W][8]
-template <int CIN, int CMID, int COUT>
-static int launch_conv3_tc(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2, const float* b2,
-                           int n, int H, int W, cudaStream_t st) {
-    using Cfg = Conv3TcCfg<CIN, CMID, COUT>;
-    auto enc = tensor_map_encoder();
-    if (!enc) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-    CUtensorMap tm;
-    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(CIN / 8), (cuuint64_t)n};
-    cuuint64_t strides[4] = {(cuuint64_t)CIN * 2, (cuuint64_t)W * CIN * 2, 16, (cuuint64_t)H * W * CIN * 2};
-    cuuint32_t box[5] = {8, (cuuint32_t)Cfg::SW, (cuuint32_t)Cfg::SH, (cuuint32_t)(CIN / 8), 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(in), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(MDS_ERR_CUDA, "cuTensorMapEncodeTiled(5d) failed (%d) n=%d H=%d W=%d C=%d", (int)r, n, H, W, CIN);
-    Conv3TcParams p;
-    p.in = in; p.out = out; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.n = n; p.H = H; p.W = W;
-    p.tiles_x = (W + Cfg::TW - 1) / Cfg::TW;
-    p.tiles_y = (H + Cfg::TH - 1) / Cfg::TH;
-    const long long tiles = (long long)p.tiles_x * p.tiles_y * n;
-    if (tiles <= 0) return MDS_OK;
-    auto kern = conv3x3_tc_kernel<CIN, CMID, COUT>;
-    ENSURE_SMEM_ATTR(kern, Cfg::SMEM);
-    int grid = num_sms();
-    if (tiles < grid) grid = (int)tiles;
-    ProfScope ps(MDS_KIND_CONV3X3, st);
-    launch_pdl(kern, dim3(grid), dim3(kTcThreads), Cfg::SMEM, st, tm, p);
-    LAUNCH_CHECK("conv3x3_tc");
     return MDS_OK;
 }
 
@@ -399,37 +354,22 @@ static int launch_conv_tc_ws(const __half* in, __half* out, const __half* w1, co
 static int launch_conv3(const __half* in, __half* out, const __half* w1, const float* b1, const __half* w2,
                         const float* b2, int n, int H, int W, int cin, int cmid, int stride, int cproj, int res,
                         cudaStream_t st, const __half* w1t = nullptr) {
-    Conv3Params p;
-    p.in = in; p.out = out; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
-    p.n = n; p.H = H; p.W = W;
-    p.Ho = (H + stride - 1) / stride; p.Wo = (W + stride - 1) / stride;
+    if (H <= 0 || W <= 0 || n < 0) return fail(MDS_ERR_INVALID, "conv3x3: bad size n=%d H=%d W=%d", n, H, W);
     if (stride == 2 && (H % 2 || W % 2)) return fail(MDS_ERR_INVALID, "conv3x3: stride-2 input must be even");
-    if (g_conv_mode >= 1 && H > 0 && W > 0 && (stride == 1 || (H % 2 == 0 && W % 2 == 0))) {
-        const bool pt = g_conv_mode == 2;
+    const bool pt = g_conv_mode == 2;
 #define CTCASE(CI, CM, CP, S, R, TH_S, TH_T, MB)                                                            \
     if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0))                          \
         return pt ? launch_conv_tc<CI, CM, CP, S, R, TH_T, true, MB>(in, out, w1, b1, w2, b2, n, H, W, st)   \
                   : launch_conv_tc<CI, CM, CP, S, R, TH_S, false, MB>(in, out, w1, b1, w2, b2, n, H, W, st);
-        if (cin == 32 && cmid == 16 && stride == 1 && cproj == 0 && res == 0)      // blocks.0.0 ConvBnAct: two CTAs per SM
-            return pt ? launch_conv_tc<32, 16, 0, 1, false, 16, true, 2, true>(in, out, w1, b1, w2, b2, n, H, W, st)     // column taps folded into N
-                      : launch_conv_tc<32, 16, 0, 1, false, 15, false, 2, false>(in, out, w1, b1, w2, b2, n, H, W, st);
-        CTCASE(16, 64, 32, 2, false, 15, 15, 1)    // blocks.1.0  EdgeResidual s2
-        CTCASE(32, 128, 32, 1, true, 15, 15, 1)    // blocks.1.1
-        CTCASE(32, 128, 48, 2, false, 3, 7, 1)     // blocks.2.0  (P in shared memory only fits with 3-row tiles)
+    if (cin == 32 && cmid == 16 && stride == 1 && cproj == 0 && res == 0)      // blocks.0.0 ConvBnAct: two CTAs per SM
+        return pt ? launch_conv_tc<32, 16, 0, 1, false, 16, true, 2, true>(in, out, w1, b1, w2, b2, n, H, W, st)     // column taps folded into N
+                  : launch_conv_tc<32, 16, 0, 1, false, 15, false, 2, false>(in, out, w1, b1, w2, b2, n, H, W, st);
+    CTCASE(16, 64, 32, 2, false, 15, 15, 1)    // blocks.1.0  EdgeResidual s2
+    CTCASE(32, 128, 32, 1, true, 15, 15, 1)    // blocks.1.1
+    CTCASE(32, 128, 48, 2, false, 3, 7, 1)     // blocks.2.0  (P in shared memory only fits with 3-row tiles)
 #undef CTCASE
-        if (pt && cin == 48 && cmid == 192 && stride == 1 && cproj == 48 && res == 1)      // blocks.2.1: 3x3 weights streamed from L2
-            return launch_conv_tc_ws<48, 192, 48>(in, out, w1, w1t, b1, w2, b2, n, H, W, st);
-    }
-    if (cin == 32 && cmid == 128 && stride == 1 && cproj == 32 && res == 1)     // blocks.1.1: tcgen05 implicit GEMM
-        return launch_conv3_tc<32, 128, 32>(in, out, w1, b1, w2, b2, n, H, W, st);
-#define C3CASE(CI, CM, S, CP, R, MB, MT) \
-    if (cin == CI && cmid == CM && stride == S && cproj == CP && res == (R ? 1 : 0)) return launch_conv3_t<CI, CM, S, CP, R, MB, MT>(p, st);
-    C3CASE(32, 16, 1, 0, false, 2, 1)      // blocks.0.0  ConvBnAct (weights in registers)
-    C3CASE(16, 64, 2, 32, false, 2, 2)     // blocks.1.0  EdgeResidual s2
-    C3CASE(32, 128, 1, 32, true, 2, 2)     // blocks.1.1 (111 KB smem, 255 regs x 128 threads: two CTAs per SM)
-    C3CASE(32, 128, 2, 48, false, 1, 1)    // blocks.2.0 (one 4-warp CTA per SM was slower here)
-    C3CASE(48, 192, 1, 48, true, 1, 1)     // blocks.2.1 (192 mid channels: two rows per warp would not fit the register file)
-#undef C3CASE
+    if (cin == 48 && cmid == 192 && stride == 1 && cproj == 48 && res == 1)      // blocks.2.1: 3x3 weights streamed from L2
+        return launch_conv_tc_ws<48, 192, 48>(in, out, w1, w1t, b1, w2, b2, n, H, W, st);
     return fail(MDS_ERR_INVALID, "conv3x3: unsupported shape cin=%d cmid=%d stride=%d cproj=%d res=%d", cin, cmid, stride, cproj, res);
 }
 

@@ -41,8 +41,8 @@ def parse():
     ap.add_argument("--tta", type=int, default=0)
     ap.add_argument("--tail-mode", type=int, default=3, choices=[0, 1, 2, 3],
                     help="MBConv tails: 3 = TMA depthwise + SE kernel + GEMM (default), 2 = depthwise+SE kernel and gating GEMM, 1 = one fused launch, 0 = round-1 path")
-    ap.add_argument("--conv-mode", type=int, default=2, choices=[0, 1, 2],
-                    help="dense 3x3 blocks: 2 conv_tc_kernel (tcgen05, expanded tensor in TMEM), 1 same with smem staging, 0 round-1 kernels (A/B)")
+    ap.add_argument("--conv-mode", type=int, default=2, choices=[1, 2],
+                    help="dense 3x3 blocks: 2 conv_tc_kernel with the expanded tensor in TMEM, 1 the same with smem staging (A/B)")
     ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 3, 4], help="encoder on one stream or as equal parts of the images on several streams (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)

@@ -239,9 +239,9 @@ int mds_set_pdl(int enabled);
  * 2: mds_k_dwconv_se (incl. the SE MLP) + mds_k_gemm_gate; 1: mds_k_mbconv_tail (ONE persistent launch);
  * 0: round-1 path mds_k_dwconv + mds_k_se_fc + mds_k_gemm_gated. */
 int mds_set_tail_mode(int mode);
-/* Which kernels run the dense 3x3 blocks (blocks.0.0 - 2.1; A/B measurements, all parity-tested).  2 (default): conv_tc_kernel
- * (TMA + tcgen05, the expanded tensor stays in tensor memory); 1: conv_tc_kernel staging the expanded tensor in shared memory;
- * 0: the round-1 kernels (mma.sync conv3x3_kernel, conv3x3_tc_kernel for blocks.1.1). */
+/* How the dense 3x3 blocks (blocks.0.0 - 2.0) keep their expanded tensor (A/B measurements, both parity-tested).  2 (default):
+ * conv_tc_kernel (TMA + tcgen05) leaves it in tensor memory as the projection's A operand and folds the column taps of blocks.0.0
+ * into N; 1: conv_tc_kernel stages it in shared memory. */
 int mds_set_conv_mode(int mode);
 /* The encoder of mds_forward / mds_forward_2d runs as n equal parts of the images on n streams (default 2: the kernels of one half
  * fill the ramps and tails of the other; handle-owned streams forked from / joined to the caller's stream; 1 = single stream). */

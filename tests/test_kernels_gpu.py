@@ -39,10 +39,9 @@ def nchw(t):
 
 
 @pytest.mark.parametrize("dtype,hflip", [("u8", 0), ("u8", 1), ("f32", 0)])
-@pytest.mark.parametrize("mode", [2, 0])
 @pytest.mark.parametrize("size", [(2, 96, 160, 80), (2, 736, 1280, 720), (3, 64, 208, 50)])
-def test_stem(lib, dtype, hflip, mode, size):
-    """mode 2: uint8 frames go through stem_tc_kernel (TMA + tcgen05); mode 0 and float input: the mma.sync stem_kernel.
+def test_stem(lib, dtype, hflip, size):
+    """uint8 frames go through stem_tc_kernel (TMA + tcgen05), float input through the mma.sync stem_kernel.
     Sizes: a small case, the real 720 -> 736 x 1280 frames (every persistent CTA loops over many tiles), and a width / height
     that is not a multiple of the 64 x 8 output tile with an odd number of stored rows."""
     from ball_action_spotting_b200._lib import MdsFrames
@@ -68,22 +67,18 @@ def test_stem(lib, dtype, hflip, mode, size):
     d_b = b.to(DEV)
     out = torch.full((n, H // 2, W // 2, 32), float("nan"), dtype=torch.float16, device=DEV)
     fr = MdsFrames(d_raw.data_ptr(), dt, 3 * stored_h * W, stored_h * W, stored_h, (H - stored_h) // 2, H, W, hflip)
-    ok(lib.mds_set_conv_mode(mode), lib)
-    try:
-        ok(lib.mds_k_stem(C.byref(fr), n, d_w.data_ptr(), d_b.data_ptr(), out.data_ptr(), None), lib)
-        torch.cuda.synchronize()
-    finally:
-        lib.mds_set_conv_mode(2)
+    ok(lib.mds_k_stem(C.byref(fr), n, d_w.data_ptr(), d_b.data_ptr(), out.data_ptr(), None), lib)
+    torch.cuda.synchronize()
     assert rel(nchw(out), ref) <= TOL
 
 
 @pytest.mark.parametrize("cin,cmid,stride,cproj,res", [(32, 16, 1, 0, 0), (16, 64, 2, 32, 0), (32, 128, 1, 32, 1),
                                                        (32, 128, 2, 48, 0), (48, 192, 1, 48, 1)])
 @pytest.mark.parametrize("hw", [(24, 40), (46, 34)])
-@pytest.mark.parametrize("mode", [2, 1, 0])
+@pytest.mark.parametrize("mode", [2, 1])
 def test_conv3x3(lib, cin, cmid, stride, cproj, res, hw, mode):
-    """mode = mds_set_conv_mode: 2 = conv_tc_kernel with the expanded tensor in tensor memory (default), 1 = staged in shared
-    memory, 0 = the round-1 kernels.  blocks.2.1 (48, 192) runs the same kernel in every mode."""
+    """mode = mds_set_conv_mode: 2 = conv_tc_kernel with the expanded tensor in tensor memory (default; blocks.0.0 with the column
+    taps folded into N), 1 = staged in shared memory.  blocks.2.1 (48, 192) runs conv_tc_ws_kernel in both modes."""
     n, (H, W) = 2, hw
     x = h16(torch.randn(n, cin, H, W, generator=gen(1)))
     w1 = h16(torch.randn(cmid, cin, 3, 3, generator=gen(2)) * (2.0 / (9 * cin)) ** 0.5)
@@ -163,8 +158,8 @@ def test_conv_tc_many_tiles(lib, cin, cmid, stride, cproj, res, hw, mode):
 
 
 def test_conv3x3_tcgen05_many_tiles(lib):
-    """blocks.1.1 at its real 184x320 resolution, 5 images: 650 halo tiles, so every persistent CTA loops over several tiles
-    and both tile buffers / both accumulators wrap their mbarrier phases."""
+    """blocks.1.1 (conv_tc_kernel<32,128,32>) at its real 184x320 resolution, 5 images: 650 halo tiles, so every persistent CTA
+    loops over several tiles and both tile buffers / both accumulators wrap their mbarrier phases."""
     cin, cmid, cproj = 32, 128, 32
     n, H, W = 5, 184, 320
     x = h16(torch.randn(n, cin, H, W, generator=gen(1)))

@@ -4,7 +4,7 @@ timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 300 python bench.py > gpurun_out/bench_r02_b4.json 2> gpurun_out/bench_r02_b4.err
 timeout 300 python bench.py --batch 32 --no-cpu-baseline > gpurun_out/bench_r02_b32.json 2>/dev/null
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_r02_reference.json 2>/dev/null
-timeout 300 python bench.py --conv-mode 0 --no-cpu-baseline > gpurun_out/bench_r02_b4_convmode0.json 2>/dev/null
+
 timeout 300 python bench.py --mode sweep > gpurun_out/sweep_r02_full_n1.json 2> gpurun_out/sweep_r02_full_n1.err
 for f in bench_r02_b4 bench_r02_b32 bench_r02_reference bench_r02_b4_convmode0 sweep_r02_full_n1; do python -c "
 import json,sys

@@ -8,7 +8,7 @@
 
 #include "../ball_action_spotting_b200/csrc/common.cuh"
 #include "../ball_action_spotting_b200/csrc/gemm_tc.cuh"
-#include "../ball_action_spotting_b200/csrc/conv3x3_tc.cuh"
+#include "../ball_action_spotting_b200/csrc/tc_helpers.cuh"
 
 using namespace mds;
 
