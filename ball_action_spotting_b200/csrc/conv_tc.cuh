@@ -343,10 +343,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, ConvTcParams p) {
         }
     } else {
         // ================= epilogue: GROUPS x 4 lane quadrants x PARTS column parts =================
-        // Each warp streams its columns of an M tile in 8-column chunks: the tcgen05.ld of chunk c+1 (and, across M tiles, of
-        // chunk 0 of the next tile) is in flight while chunk c goes through SiLU, so the TMEM read port (64 B / clk), the SFU
-        // pipe and the tensor core overlap.  E2 (projection accumulator -> + residual -> global) of M tile t-1 is issued after
-        // E1 of tile t: its MMA ran on the tensor core meanwhile.
+        // Group e takes the M tiles t with t % 2 == e, so one group's SFU-bound E1 phase covers the other's waits.  Each warp
+        // streams its columns of an M tile in 8-column chunks: the tcgen05.ld of chunk c+1 is in flight while chunk c goes through
+        // SiLU (a tcgen05.ld + wait::ld round trip is ~180 clocks whatever its width, tools/tmem_probe.cu).  Order per M tile:
+        // E1(t) [D1 -> SiLU -> P], E2 of the group's previous tile [D2 + residual -> global; its projection ran on the tensor core
+        // meanwhile, and the projection of THIS tile waits for that accumulator], then the first chunk of the group's next tile.
         const int q = warp & 3;                         // TMEM lane quadrant
         const int ew = (warp - 2) >> 2;                 // 0 .. GROUPS * PARTS - 1
         const int grp = ew / Cfg::PARTS, part = ew - grp * Cfg::PARTS;

@@ -4,12 +4,14 @@
 // to stream A once, write C once and keep the bias+SiLU epilogue off the critical path:
 //   * a CTA owns a 128-row A tile (K <= 192 -> at most three 128x64 blocks, resident in smem, double-buffered
 //     across row tiles) and sweeps ALL N tiles of it, streaming only W blocks (L2-resident) through a TMA ring;
-//   * warp 0 / lane 0 : TMA producer (cp.async.bulk.tensor 2D, 128-byte swizzle, OOB rows / K tail zero-filled
-//     by the TMA unit, mbarrier expect_tx);
-//   * warp 1          : TMEM allocator; lane 0 issues tcgen05.mma (M=128, N=BN, K=16, fp16 -> fp32 in TMEM) and
+//   * warp 0           : TMA producer (cp.async.bulk.tensor 2D, 128-byte swizzle, OOB rows / K tail zero-filled by the TMA unit,
+//     mbarrier expect_tx); the whole warp runs the loops converged and one lane elected by elect.sync issues (under `lane == 0`
+//     ptxas wraps every UTMALDG / UTCHMMA in an election loop of 60-90 clocks);
+//   * warp 1           : TMEM allocator and MMA issuer, same scheme: tcgen05.mma (M=128, N=BN, K=16, fp16 -> fp32 in TMEM) and
 //     tcgen05.commit to release smem and to publish finished accumulators;
-//   * warps 2-17      : epilogue — tcgen05.ld 16 accumulator columns per request, bias + SiLU in fp32, one rounding
-//     to fp16, one 32-byte (full sector) st.global.v8 per request; no smem staging;
+//   * warps 2-17       : epilogue, two groups of 8 (one per accumulator): a warp streams 16-column chunks - the tcgen05.ld (and
+//     residual load) of the next chunk in flight, SiLU with one reciprocal per four values, one rounding to fp16, one 32-byte
+//     (full sector) st.global.v8 per chunk; no smem staging; templated on ACT / RES so that only two chunk buffers are live;
 //   * the bias is added by the tensor core: one extra K=16 MMA per tile multiplies a constant "ones" A tile with a
 //     [N][64] fp16 matrix holding bias as a hi/lo pair (exact to ~2^-22), so the epilogue has no loads at all;
 //   * two accumulators (2*BN TMEM columns): the epilogue of tile i overlaps the MMAs of tile i+1.

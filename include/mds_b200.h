@@ -107,8 +107,16 @@ int mds_nchw32_to_nhwc16(const float* src, void* dst, int n, int C, int P, void*
 int mds_nhwc16_to_nchw32(const void* src, float* dst, int n, int C, int P, void* stream);
 
 /* ---- per-kernel entry points (parity tests, ncu) ---- */
-/* wh: fp16 [2][32][32] = (hi, lo) x cout x k, k = (ci*3 + r)*3 + s, columns 27..31 zero (packer.stem_weights) */
+/* Stem (frames.py:7-31 pad + /255, timm conv_stem + bn1 + SiLU; multidim_stacker.py:214): out fp16 [n][H/2][W/2][32].
+ * wh: fp16 [2][32][32] = (hi, lo) x cout x k, k = (ci*3 + r)*3 + s, columns 27..31 zero (packer.stem_weights).
+ * uint8 frames run stem_tc_kernel (TMA + tcgen05) and need W >= 144, W / plane_stride / img_stride multiples of 16 and a 16-byte
+ * aligned base; float32 frames run the mma.sync gather kernel. */
 int mds_k_stem(const MdsFrames* frames, int n_images, const void* wh, const float* bias, void* out, void* stream);
+/* Dense 3x3 blocks of timm tf_efficientnetv2_b0 (built at multidim_stacker.py:166-176), NHWC fp16, BN folded:
+ * ConvBnAct (cproj = 0): out = SiLU(conv3x3(in) + b1); EdgeResidual: out = conv1x1(SiLU(conv3x3_stride(in) + b1)) + b2 (+ in if res).
+ * w1 [cmid][9*cin] (k = (r*3+s)*cin + ci), w2 [cproj][cmid].  Supported (cin, cmid, stride, cproj, res): (32,16,1,0,0), (16,64,2,32,0),
+ * (32,128,1,32,1), (32,128,2,48,0) -> conv_tc_kernel; (48,192,1,48,1) -> conv_tc_ws_kernel; anything else is MDS_ERR_INVALID.
+ * stride 2 = TF-SAME on an even H, W (pad bottom / right). */
 int mds_k_conv3x3(const void* in, void* out, const void* w1, const float* b1, const void* w2, const float* b2,
                   int n, int H, int W, int cin, int cmid, int stride, int cproj, int res, void* stream);
 /* bias_mat (optional): [N][64] fp16, col 0 = fp16(bias), col 1 = fp16(bias - col 0); selects the tcgen05 kernel for
