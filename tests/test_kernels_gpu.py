@@ -39,11 +39,11 @@ def nchw(t):
 
 
 @pytest.mark.parametrize("dtype,hflip", [("u8", 0), ("u8", 1), ("f32", 0)])
-@pytest.mark.parametrize("size", [(2, 96, 160, 80), (2, 736, 1280, 720), (3, 64, 208, 50)])
+@pytest.mark.parametrize("size", [(2, 96, 160, 80), (2, 736, 1280, 720), (3, 64, 208, 50), (2, 72, 160, 60)])
 def test_stem(lib, dtype, hflip, size):
     """uint8 frames go through stem_tc_kernel (TMA + tcgen05), float input through the mma.sync stem_kernel.
     Sizes: a small case, the real 720 -> 736 x 1280 frames (every persistent CTA loops over many tiles), and a width / height
-    that is not a multiple of the 64 x 8 output tile with an odd number of stored rows."""
+    that is not a multiple of the 64 x 8 output tile, and 36 output rows (the last tile has two of its four M tiles)."""
     from ball_action_spotting_b200._lib import MdsFrames
     n, H, W, sh = size
     w = torch.randn(32, 3, 3, 3, generator=gen(1)) * 0.3
