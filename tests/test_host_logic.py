@@ -251,3 +251,110 @@ def test_accounting_is_consistent_across_tail_modes():
     assert abs(dw["dwconv2d"] / (5 * 102.3e6) - 1) < 0.01 and abs(dw["dwconv3d"] / 42.4e6 - 1) < 0.01   # SURVEY 8(d) DW-only bytes
     # one launch of every encoder kernel per image chunk: 1 stem + 5 conv3x3 + 16 x (pw, dw, se, pwl) + proj = 71 (mode 0)
     assert len(acc.encoder_launches(736, 1280, 720, tail_mode=0)) == 71 and len(acc.encoder_launches(736, 1280, 720, tail_mode=1)) == 39
+
+
+def test_stem_tc_operand_layout_reproduces_the_conv():
+    """CPU emulation of stem_tc_kernel's operands (csrc/stem_tc.cuh): the K order k' = (ci*3 + r)*4 + s with a zero-weight fourth slot,
+    the two-pixels-per-thread byte gather (pixel A = x0 x1 x2 [x3], pixel B = x2 x3 x4 [x5]), the mirrored tile of the hflip TTA
+    (tile byte j = logical column 2*ox0 + 143 - j) and the weight tile built from packer.stem_weights.  The dot products must equal
+    the TF-SAME stride-2 convolution of the zero-padded, /255-normalised frames (frames.py:7-31 + timm conv_stem)."""
+    import torch.nn.functional as F
+    from ball_action_spotting_b200.packer import stem_weights
+    g = torch.Generator().manual_seed(0)
+    W_, stored_h, H = 160, 20, 24
+    pad_top = (H - stored_h) // 2
+    raw = torch.randint(0, 256, (3, stored_h, W_), dtype=torch.uint8, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.3
+    wh = stem_weights(w).double()                                   # [2][32][32], k = (ci*3 + r)*3 + s
+    wk = torch.zeros(2, 32, 48, dtype=torch.float64)                # kernel weight tile: k' = combo*4 + s, combo = ci*3 + r
+    for combo in range(9):
+        for s in range(3):
+            wk[:, :, combo * 4 + s] = wh[:, :, combo * 3 + s]
+    x = F.pad(raw.double(), (0, 0, pad_top, H - stored_h - pad_top))                       # zero rows = TMA out-of-bounds fill
+    IW = 144
+    for hflip in (0, 1):
+        xin = x.flip(-1) if hflip else x
+        ref = F.conv2d(F.pad(xin[None] / 255.0, (0, 1, 0, 1)), w.double(), stride=2)[0]   # [32][H/2][W/2]
+        for ox0 in (0, 64):
+            start = W_ - IW - 2 * ox0 if hflip else 2 * ox0                               # TMA x coordinate of the tile
+            for oy in (0, 5, H // 2 - 1):
+                tile = torch.zeros(3, 3, IW, dtype=torch.float64)                         # rows 2*oy + r of the three planes
+                for r in range(3):
+                    y = 2 * oy + r
+                    for j in range(IW):
+                        xx = start + j
+                        if 0 <= xx < W_ and y < H:
+                            tile[:, r, j] = x[:, y, xx]
+                for cp in (0, 7, 31):                                                     # pixel pair (2cp, 2cp+1) of the tile row
+                    a = torch.zeros(2, 48, dtype=torch.float64)
+                    for combo in range(9):
+                        ci, r = divmod(combo, 3)
+                        row = tile[ci, r]
+                        if hflip:
+                            xs = [row[143 - (4 * cp + i)] for i in range(6)]
+                        else:
+                            xs = [row[4 * cp + i] for i in range(6)]
+                        a[0, combo * 4:combo * 4 + 4] = torch.stack(xs[0:4])               # x0 x1 x2 [x3]
+                        a[1, combo * 4:combo * 4 + 4] = torch.stack(xs[2:6])               # x2 x3 x4 [x5]
+                    acc = a @ (wk[0] + wk[1]).t()                                          # [2 pixels][32 cout]
+                    for px in range(2):
+                        ox = ox0 + 2 * cp + px
+                        if ox < W_ // 2:
+                            got = acc[px] / 255.0
+                            assert torch.allclose(got, ref[:, oy, ox], rtol=0, atol=2e-6), (hflip, ox0, oy, cp, px)
+
+
+def test_conv_tc_index_arithmetic():
+    """CPU emulation of conv_tc_kernel's implicit-GEMM addressing (csrc/conv_tc.cuh) on a random single-channel image:
+    (a) stride 2: the input is read as its four (row, column) parity phases, each a dense (TW+1) x (TH+1) tile with TMA zero fill, and
+        tap (r, s) of output pixel p (linear index in the phase tile) is phase (r&1, s&1) at p + (r>>1)*(TW+1) + (s>>1);
+    (b) stride 1 with the column taps folded into N: D[p][s] = sum_r in[p + r*PW] * w[r][s] on the UNSHIFTED rows of a PW = 32 wide tile,
+        and output column c of a tile row is D[c][0] + D[c+1][1] + D[c+2][2] (lanes c, c+1, c+2 of one warp)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    H, W = 20, 44
+    x = torch.randn(H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 3, generator=g, dtype=torch.float64)
+    # (a) stride 2, TF-SAME on even sizes = pad bottom / right
+    ref2 = F.conv2d(F.pad(x[None, None], (0, 1, 0, 1)), w[None, None], stride=2)[0, 0]
+    TW, TH = 8, 4
+    PW, PH = TW + 1, TH + 1
+    for y0 in range(0, H // 2, TH):
+        for x0 in range(0, W // 2, TW):
+            phases = torch.zeros(4, PH * PW + PW + 2, dtype=torch.float64)      # + slack: the last M tile over-reads
+            for py in range(2):
+                for px in range(2):
+                    for yy in range(PH):
+                        for xx in range(PW):
+                            iy, ix = 2 * (y0 + yy) + py, 2 * (x0 + xx) + px
+                            if iy < H and ix < W:                                # out of bounds = TMA zero fill
+                                phases[py * 2 + px, yy * PW + xx] = x[iy, ix]
+            for ry in range(TH):
+                for cx in range(TW):
+                    oy, ox = y0 + ry, x0 + cx
+                    if oy >= H // 2 or ox >= W // 2:
+                        continue
+                    p = ry * PW + cx
+                    acc = sum(w[r, s] * phases[(r & 1) * 2 + (s & 1), p + (r >> 1) * PW + (s >> 1)] for r in range(3) for s in range(3))
+                    assert abs(acc - ref2[oy, ox]) < 1e-12
+    # (b) stride 1, pad 1, column taps folded into N
+    ref1 = F.conv2d(x[None, None], w[None, None], padding=1)[0, 0]
+    TW, TH, PW = 30, 16, 32
+    for y0 in range(0, H, TH):
+        for x0 in range(0, W, TW):
+            tile = torch.zeros((TH + 2) * PW, dtype=torch.float64)
+            for yy in range(TH + 2):
+                for xx in range(PW):
+                    iy, ix = y0 - 1 + yy, x0 - 1 + xx
+                    if 0 <= iy < H and 0 <= ix < W:
+                        tile[yy * PW + xx] = x[iy, ix]
+            for ry in range(TH):
+                D = torch.zeros(PW, 3, dtype=torch.float64)                       # one tile row = one warp = 32 lanes
+                for lane in range(PW):
+                    p = ry * PW + lane
+                    for s in range(3):
+                        D[lane, s] = sum(tile[p + r * PW] * w[r, s] for r in range(3))
+                for c in range(TW):
+                    oy, ox = y0 + ry, x0 + c
+                    if oy < H and ox < W:
+                        assert abs(D[c, 0] + D[c + 1, 1] + D[c + 2, 2] - ref1[oy, ox]) < 1e-12
