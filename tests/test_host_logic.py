@@ -358,3 +358,35 @@ def test_conv_tc_index_arithmetic():
                     oy, ox = y0 + ry, x0 + c
                     if oy < H and ox < W:
                         assert abs(D[c, 0] + D[c + 1, 1] + D[c + 2, 2] - ref1[oy, ox]) < 1e-12
+
+
+def test_silu4_algebra_and_clamp():
+    """float32 emulation of silu4 (csrc/common.cuh): SiLU of four values with one reciprocal, 1/(1+e_i) = prod_{j != i}(1+e_j) / prod_j(1+e_j),
+    inputs clamped at -20 so that the product of the four (1 + e) factors stays finite.  Against float64 SiLU: relative error < 2e-6 for
+    x >= -20 (before the SFU approximations, which add ~2 ulp; fp16 storage rounds at 4.9e-4) and an absolute error below the smallest fp16 subnormal beyond the clamp."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(0, 3, 4000), rng.uniform(-20, 20, 4000), np.array([-20.0, -19.999, 0.0, 1e-8, 30.0, 88.0, -1e-3, 5.5])])
+    x = x[: len(x) // 4 * 4].astype(np.float32).reshape(-1, 4)
+    tail = np.array([[-25.0, -100.0, -1e4, -20.5], [-3e38, 0.0, 3.0, -50.0]], dtype=np.float32)
+
+    def silu4(v):
+        v = np.maximum(v, np.float32(-20.0))
+        e = np.exp2((v * np.float32(-1.4426950408889634)).astype(np.float32)).astype(np.float32)
+        d = (np.float32(1.0) + e).astype(np.float32)
+        p01, p23 = d[:, 0] * d[:, 1], d[:, 2] * d[:, 3]
+        r = (np.float32(1.0) / (p01 * p23)).astype(np.float32)
+        r01, r23 = r * p23, r * p01
+        out = np.stack([v[:, 0] * (r01 * d[:, 1]), v[:, 1] * (r01 * d[:, 0]), v[:, 2] * (r23 * d[:, 3]), v[:, 3] * (r23 * d[:, 2])], 1)
+        return out.astype(np.float32)
+
+    got = silu4(x).astype(np.float64)
+    xd = x.astype(np.float64)
+    ref = xd / (1.0 + np.exp(-xd))
+    assert np.all(np.isfinite(got))
+    nz = np.abs(ref) > 1e-30
+    assert np.max(np.abs(got[nz] - ref[nz]) / np.abs(ref[nz])) < 2e-6
+    gt = silu4(tail).astype(np.float64)
+    td = tail.astype(np.float64)
+    rt = td / (1.0 + np.exp(-np.maximum(td, -700.0)))
+    assert np.all(np.isfinite(gt)) and np.max(np.abs(gt - rt)) < 6e-8          # < the smallest fp16 subnormal (5.96e-8)
