@@ -392,3 +392,56 @@ def test_silu4_algebra_and_clamp():
     beyond = td < -20.0
     assert np.all(np.isfinite(gt)) and np.max(np.abs(gt[beyond] - rt[beyond])) < 6e-8     # < the smallest fp16 subnormal (5.96e-8)
     assert np.max(np.abs(gt[~beyond] - rt[~beyond])) < 1e-6
+
+
+def test_tcgen05_epilogue_partitions_cover_every_column_once():
+    """Mirrors of the index arithmetic of the tensor-memory epilogues: every accumulator column is read by exactly one warp.
+    gemm_tc_kernel: warp `half` of `nhalf` takes the 16-column chunks half + nhalf*k, k < nk = ceil((BN/16 - half) / nhalf).
+    conv_tc_kernel: PARTS warps per quadrant take CMID/PARTS consecutive columns in 8-column chunks; the projection's 16-column groups
+    g = part + PARTS*j.  conv_tc_ws_kernel: 4 parts x 48 columns, packed P columns (col / 2) stay inside the low half of the accumulator."""
+    for BN in range(32, 257, 16):
+        for nhalf in (1, 2):
+            ngroups = BN // 16
+            seen = []
+            for half in range(nhalf):
+                nk = (ngroups - half + nhalf - 1) // nhalf
+                seen += [half + nhalf * k for k in range(nk)]
+            assert sorted(seen) == list(range(ngroups)), (BN, nhalf)
+    for cmid, cproj in ((16, 0), (64, 32), (128, 32), (128, 48)):
+        parts = 2 if cmid >= 32 else 1
+        cols = cmid // parts
+        assert cols % 16 == 0 and (cols // 8) % 2 == 0
+        covered = sorted(c for part in range(parts) for ch in range(cols // 8) for c in range(part * cols + ch * 8, part * cols + ch * 8 + 8))
+        assert covered == list(range(cmid))
+        if cproj:
+            ng2 = cproj // 16
+            nj = 2 if ng2 > parts else 1
+            groups = sorted(part + parts * j for part in range(parts) for j in range(nj) if part + parts * j < ng2)
+            assert groups == list(range(ng2))
+    cmid, parts = 192, 4
+    cols = cmid // parts
+    pcols = sorted(c for part in range(parts) for j in range(cols // 16) for c in range((part * cols + j * 16) // 2, (part * cols + j * 16) // 2 + 8))
+    assert pcols == list(range(cmid // 2))                  # 96 packed columns = the low half of the 192-column accumulator
+
+
+def test_conv_tc_tile_geometry_stays_inside_the_tile_allocation():
+    """ConvTcCfg / ConvWsCfg (csrc/conv_tc.cuh, conv_tc_ws.cuh): the A operand of M tile m, tap (r, s) starts at pixel m*128 + off and spans
+    128 rows; with the OVER slack the last M tile never reads past the allocation of its plane set."""
+    # (stride, TW, TH, fold)
+    for stride, TW, TH, fold in ((1, 30, 16, True), (1, 32, 15, False), (2, 32, 15, False), (2, 32, 7, False), (2, 32, 3, False)):
+        PW = TW + 2 if stride == 1 else TW + 1
+        PH = TH + 2 if stride == 1 else TH + 1
+        PIX = PW * PH
+        MT = (TH * PW + 127) // 128
+        max_off = (2 * PW + 2) if stride == 1 else (PW + 1)
+        over = max(0, MT * 128 + max_off - PIX)
+        offs = [r * PW for r in range(3)] if fold else ([r * PW + s for r in range(3) for s in range(3)] if stride == 1
+                                                        else [(r >> 1) * PW + (s >> 1) for r in range(3) for s in range(3)])
+        last_read = (MT - 1) * 128 + max(offs) + 127
+        assert last_read < PIX + over, (stride, TW, TH, fold)
+        if fold:
+            assert PW == 32 and TH * PW % 128 == 0 and last_read < PIX      # tile rows = TMEM lane quadrants, nothing read past the tile
+        # every valid output pixel of the tile lies in an M tile that is computed
+        rows = TH
+        nm = (rows * PW + 127) // 128
+        assert (rows - 1) * PW + (TW - 1) < nm * 128
